@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on B200: KKT factor+solve FP64 TFLOP/s (cfg3, n=8192
+normal-equations reduction) plus batched IPM solves/s (cfg4) in the same JSON line.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    the reference's own CPU path
+
+A "step" of the headline metric is one pass of the hot path over the resident condensed
+matrix K = Hx + M^T W M of the cfg3 QP: out-of-place LDL^T (root-free Cholesky) + two
+triangular solves (predictor and corrector right-hand sides), i.e. N^3/3 + 2*2N^2 flops --
+the linear algebra of one IPM iteration.  `value` is that with K resident in HBM; `e2e` is
+the same metric through the solver C ABI from pinned HOST buffers (ipmz_create uploads the
+QP, ipmz_solve runs the whole IPM loop incl. assembly, ipmz_get_iterate reads the answer).
+N > 1: the single large KKT does not shard ("replicas only") so every rank runs a
+replica; the batched workload shards 4096 QPs by problem index with no collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "kkt_factor_solve_fp64_tflops"
+UNIT = "TFLOP/s"
+CFG3 = dict(n=8192, m=4096, seed=3)
+CFG4 = dict(n=256, m=128, count=4096, seed0=1000)
+
+
+def flops_factor_solve(N, nrhs=2):
+    return N ** 3 / 3.0 + nrhs * 2.0 * N * N
+
+
+def make_cfg3(n, m, seed):
+    """cfg3 inputs: Q = 3I + sym N(0,1/n), A ~ N(0,1/n), l/u = A x0 -+ 0.25, box [-1,1]."""
+    rng = np.random.default_rng(seed)
+    S = rng.standard_normal((n, n)) / np.sqrt(n)
+    Q = 3.0 * np.eye(n) + 0.5 * (S + S.T)
+    del S
+    c = rng.standard_normal(n)
+    A = rng.standard_normal((m, n)) / np.sqrt(n)
+    x0 = rng.uniform(-0.5, 0.5, n)
+    mid = A @ x0
+    return dict(Q=Q, c=c, A=A, l_A=mid - 0.25, u_A=mid + 0.25, l_x=-np.ones(n), u_x=np.ones(n))
+
+
+def condensed_block(d, ns):
+    """Leading ns x ns block of K = Hx + A^T W A at the reference's initial point (all slacks
+    and duals 1: Hx = Q + 2I, W = 2I) -- the CPU sample matrix of the reference arm."""
+    A = d["A"][:, :ns]
+    return np.ascontiguousarray(d["Q"][:ns, :ns] + 2.0 * np.eye(ns) + 2.0 * (A.T @ A))
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle/_ref = unmodified sources),
+    one single-threaded replica per host core, on a bounded sample of the cfg3 workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    import oracle_lib as ol
+    kind = "reference" if ol.have_ref() else "port"
+    ns = args.sample_n
+    d = make_cfg3(CFG3["n"] if not args.quick else 2 * ns, CFG3["m"] if not args.quick else ns, CFG3["seed"])
+    K = condensed_block(d, ns)
+    b = np.random.default_rng(11).standard_normal(ns)
+    cores = args.cores or os.cpu_count() or 1
+    steps, warm = args.steps, args.warmup
+
+    def worker(q):
+        L = ol.ref() if kind == "reference" else ol.port()
+        fac = L.ref_ldlt if kind == "reference" else L.orc_ldlt
+        sol = L.ref_solve_ldlt if kind == "reference" else L.orc_solve_ldlt
+        Lm, D = np.zeros((ns, ns)), np.zeros(ns)
+        times = []
+        for it in range(warm + steps):
+            t0 = time.perf_counter()
+            fac(ns, ol._ptr(K), ol._ptr(Lm), ol._ptr(D))
+            for _ in range(2):
+                x = b.copy()
+                sol(ns, ol._ptr(Lm), ol._ptr(D), ol._ptr(x))
+            times.append(time.perf_counter() - t0)
+        q.put((sum(times[warm:]), float(np.max(np.abs(K @ x - b)))))
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(q,)) for _ in range(cores)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    outs = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    tmax = max(o[0] for o in outs)
+    value = cores * steps * flops_factor_solve(ns) / tmax * 1e-12
+    sample = ("ldlt_decomposition + 2x overwriting_solve_ldlt on the leading %dx%d block of the cfg3 "
+              "condensed KKT, one single-threaded replica per core" % (ns, ns))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": tmax / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "cfg3 sample: n=%d leading block of the n=8192 m=4096 condensed KKT" % ns,
+                   "residual": max(o[1] for o in outs), "wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import ipm_zoo_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available() and z.device_count() > 0, "bench needs a GPU: no CPU fallback"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n, m = (CFG3["n"], CFG3["m"]) if not args.quick else (1024, 512)
+    N = n
+    d = make_cfg3(n, m, CFG3["seed"])
+    peak = z.fp64_peak_tflops(local)
+
+    # ---- headline: device-resident factor + 2 solves on the condensed cfg3 matrix ----
+    prob = z.Problem(d["Q"], d["c"], d["A"], d["l_A"], d["u_A"], None, None, d["l_x"], d["u_x"])
+    opt = z.Options(reduction=z.NORMAL, device=local)
+    s = z.Solver(prob, opt)
+    Kc = s.assemble()
+    s.close()
+    fac = z.Factor(N, device=local)
+    fac.set_matrix(Kc)
+    rhs = np.random.default_rng(11).standard_normal(N)
+    fac.set_rhs(rhs)
+    for _ in range(args.warmup):
+        fac.run(1, 2)
+    x = fac.solution()
+    resid = float(np.max(np.abs(Kc @ x - rhs)) / np.max(np.abs(rhs)))
+    launches0 = z.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ms_dev = fac.run(args.steps, 2)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = z.launch_count() - launches0
+    ms_max = allmax(ms_dev)
+    flops_step = flops_factor_solve(N)
+    value = world * args.steps * flops_step / (ms_max * 1e-3) * 1e-12
+
+    prof = fac.profile()
+    syrk_tf = prof["syrk_flops"] / (prof["syrk_ms"] * 1e-3) * 1e-12 if prof["syrk_ms"] > 0 else 0.0
+    step_ms = ms_dev / args.steps
+    roofline = {
+        "bound": "tensor", "kernel": "k_syrk_ldl (FP64 DMMA trailing update)",
+        "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
+        "traffic": None,
+        "peak_source": "live DMMA issue-rate probe (ipmz_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 "
+                       "entry; cuBLAS DGEMM 8192^3 on this pool = 36.0 TFLOP/s (profiles/r01_fp64_ceilings.log)",
+        "flops_per_launch": prof["syrk_flops"] / max(1, prof["syrk_launches"]),
+        "launches_per_step": prof["syrk_launches"],
+        "ms_per_launch": prof["syrk_ms"] / max(1, prof["syrk_launches"]),
+        "share_of_step": prof["syrk_ms"] / step_ms if step_ms else None,
+        "diag_ms": prof["diag_ms"], "panel_ms": prof["panel_ms"], "syrk_ms": prof["syrk_ms"],
+        "whole_step_frac_of_peak": (flops_step / (step_ms * 1e-3) * 1e-12) / peak if peak else None,
+    }
+    fac.close()
+    del Kc
+
+    # ---- e2e: whole IPM solve through the C ABI from pinned host buffers ----
+    pin = {}
+    for k in ("Q", "c", "A", "l_A", "u_A", "l_x", "u_x"):
+        pin[k] = z.pinned_empty(d[k].shape)
+        pin[k][...] = d[k]
+    pprob = z.Problem(pin["Q"], pin["c"], pin["A"], pin["l_A"], pin["u_A"], None, None, pin["l_x"], pin["u_x"])
+    h2d = sum(int(v.nbytes) for v in pin.values())
+    e2e_runs = []
+    for rep in range(1 + max(1, min(args.steps, 2))):
+        barrier()
+        t0 = time.perf_counter()
+        sv = z.Solver(pprob, opt)
+        r = sv.solve()
+        it = sv.iterate()
+        t1 = time.perf_counter() - t0
+        sv.close()
+        if rep > 0:
+            e2e_runs.append((t1, r))
+    t_e2e = allmax(float(np.mean([t for t, _ in e2e_runs])))
+    r = e2e_runs[-1][1]
+    e2e_val = world * r.iterations * flops_factor_solve(N) / t_e2e * 1e-12
+    e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(it.nbytes),
+           "seconds": t_e2e, "iterations": r.iterations, "converged": r.converged, "f": r.f,
+           "device_loop_ms": r.solve_ms,
+           "call": "ipmz_create (H2D of Q, A, bounds) + ipmz_solve (full Mehrotra loop, normal reduction) + "
+                   "ipmz_get_iterate; flops counted = iterations x (N^3/3 + 4N^2), assembly flops not counted"}
+
+    # ---- batched IPM solves/s (cfg4), sharded by problem index, no collective ----
+    batched = None
+    if not args.no_batched:
+        batched = bench_batched(z, args, world, rank, local, barrier, allmax, allsum)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference arm in a subprocess ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0", "--sample-n", str(args.sample_n)] + (["--quick"] if args.quick else []),
+                                 capture_output=True, text=True, timeout=900)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # the baseline is reported, never substituted
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg3: dense QP n=%d m=%d, normal-equations reduction; step = out-of-place LDL^T "
+                                   "(root-free Cholesky) of the condensed KKT + 2 triangular solves" % (n, m),
+                       "N": N, "flops_per_step": flops_step, "parallelism": "replicas x%d" % world,
+                       "l2": "input matrix %.0f MB > 126 MB L2, re-read from HBM every step" % (N * N * 8 / 1e6),
+                       "solution_residual": resid, "wall_s": wall},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "batched": batched,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
+    import problems as P
+    total = CFG4["count"] if not args.quick else 64
+    n, m = CFG4["n"], CFG4["m"]
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    cnt = hi - lo
+    keys = ("Q", "c", "A", "l_A", "u_A", "l_x", "u_x")
+    shapes = dict(Q=(cnt, n, n), c=(cnt, n), A=(cnt, m, n), l_A=(cnt, m), u_A=(cnt, m), l_x=(cnt, n), u_x=(cnt, n))
+    pin = {k: z.pinned_empty(shapes[k]) for k in keys}
+    for i in range(cnt):
+        q = P.ineq_box(n, m, CFG4["seed0"] + lo + i, kind="shift")
+        for k in keys:
+            pin[k][i] = getattr(q, k)
+    bp = z.Problem(pin["Q"], pin["c"], pin["A"], pin["l_A"], pin["u_A"], None, None, pin["l_x"], pin["u_x"])
+    red = z.NORMAL if args.batch_reduction == "normal" else z.AUGMENTED
+    bs = z.BatchSolver(bp, cnt, z.Options(reduction=red, device=local))
+    xout = z.pinned_empty((cnt, n))
+    h2d = sum(int(v.nbytes) for v in pin.values())
+    dev_ms, e2e_s, iters = [], [], None
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        bs.upload()
+        res, ms = bs.solve(per_problem=(rep == 2))
+        bs.x(xout)
+        e2e_s.append(time.perf_counter() - t0)
+        dev_ms.append(ms)
+        if res is not None:
+            iters = [r.iterations for r in res]
+            conv = sum(1 for r in res if r.converged)
+    bs.close()
+    t_dev = allmax(min(dev_ms[1:])) * 1e-3
+    t_e2e = allmax(min(e2e_s[1:]))
+    nconv = allsum(conv)
+    return {"metric": "ipm_solves_per_sec", "workload": "cfg4: %d independent QPs n=%d m=%d (ineq + box), sharded by "
+            "problem index over %d GPU(s), no collective" % (total, n, m, world), "reduction": args.batch_reduction,
+            "value": total / t_dev, "unit": "solves/s", "scaling": "strong",
+            "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(xout.nbytes), "seconds": t_e2e},
+            "device_seconds": t_dev, "converged": int(nconv), "iterations_mean": float(np.mean(iters)),
+            "iterations_max": int(np.max(iters))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sample-n", type=int, default=2048, help="CPU sample size of the reference arm")
+    ap.add_argument("--cores", type=int, default=0)
+    ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch-reduction", default="normal", choices=["normal", "augmented"])
+    ap.add_argument("--quick", action="store_true", help="small sizes (debug only; not a valid bench line)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,175 @@
+/*
+ * include/ipmz.h -- C ABI of the B200-native ipm-zoo numerical interior-point hot path.
+ *
+ * The reference (albfre/ipm-zoo) has no FFI: its boundary for this path is the C++ API of
+ * namespace NumericalOptimization.  This header is the thin C layer a C++ adapter with the
+ * reference's own class/function names binds to (ipm-zoo_b200/host/):
+ *
+ *   reference interface (file:line)                                   replaced by
+ *   ----------------------------------------------------------------  -------------------------
+ *   struct Data                EnvironmentBuilder.h:7-17              ipmz_problem
+ *   SymbolicOptimization::Settings  SymbolicOptimization.h:58-64      ipmz_problem.{ineq_bounds,
+ *                                                                      var_bounds,equalities}
+ *   build_environment (initial point) EnvironmentBuilder.cpp:34-73    ipmz_create (device-side)
+ *   Optimizer::Optimizer       Optimizer.h:15-18, Optimizer.cpp:27-61 ipmz_create
+ *   Optimizer::solve           Optimizer.h:20, Optimizer.cpp:63-220   ipmz_solve
+ *   Environment as in/out state Evaluation.h:22                       ipmz_set_iterate / ipmz_get_iterate
+ *   stdout "iter:" / "b:" lines Optimizer.cpp:131-132, :359           ipmz_result + ipmz_get_trace
+ *   LinearSolvers::ldlt_decomposition     LinearSolvers.h:11          ipmz_ldlt_decomposition
+ *   LinearSolvers::overwriting_solve_ldlt LinearSolvers.h:16-17       ipmz_overwriting_solve_ldlt
+ *   (batched independent QPs: no reference counterpart, north_star)   ipmz_batch_*
+ *
+ * Conventions: every entry point returns 0 on success and a non-zero ipmz_status otherwise;
+ * ipmz_last_error() gives the message.  The C++ adapter turns non-zero into
+ * Utils::AssertionError-compatible std::logic_error (reference convention,
+ * include/Utils/Assert.h:7-12).  No exceptions or C++ types cross this boundary.  Host
+ * buffers are caller-owned; device buffers are library-owned and live until *_destroy.
+ * All matrices are dense row-major IEEE FP64.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with IPMZ_ERR_CUDA.
+ *
+ * Packed iterate layout (length ipmz_iterate_len = 5n + 6 m_ineq + 6 m_eq), names as in
+ * SymbolicOptimization.h:5-26:
+ *   x[n] lamA[mi] s[mi] lamg[mi] lamh[mi] g[mi] h[mi]
+ *   lamC[me] t[me] lamv[me] lamw[me] v[me] w[me]  lamy[n] lamz[n] y[n] z[n]
+ */
+#ifndef IPMZ_H
+#define IPMZ_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  IPMZ_OK = 0,
+  IPMZ_ERR_ARG = 1,        /* bad argument / unsupported Settings combination */
+  IPMZ_ERR_CUDA = 2,       /* CUDA runtime failure or no device */
+  IPMZ_ERR_ALLOC = 3,
+  IPMZ_ERR_INDEFINITE = 4, /* reference: solve_indefinite_() == ASSERT(false), Optimizer.cpp:75 */
+  IPMZ_ERR_BOUNDS = 5      /* reference: ASSERT(l < u), EnvironmentBuilder.cpp:10-17 */
+} ipmz_status;
+
+enum { IPMZ_BOUNDS_NONE = 0, IPMZ_BOUNDS_LOWER = 1, IPMZ_BOUNDS_UPPER = 2, IPMZ_BOUNDS_BOTH = 3 };
+
+/* Which reduction of the Newton system is assembled and factorized (north_star). */
+enum {
+  IPMZ_REDUCTION_AUGMENTED = 0, /* quasi-definite [[Hx, M^T],[M, -W^-1]], LDL^T, N = n+m   */
+  IPMZ_REDUCTION_NORMAL = 1     /* primal condensed Hx + M^T W M, root-free Cholesky, N = n */
+};
+
+typedef struct {
+  int n;       /* variables */
+  int m_ineq;  /* rows of A_ineq */
+  int m_eq;    /* rows of A_eq (handled as EqualityHandling::SlackedSlacks) */
+  const double* Q;   /* n x n, symmetric */
+  const double* c;   /* n */
+  const double* A;   /* m_ineq x n */
+  const double* l_A; /* m_ineq */
+  const double* u_A; /* m_ineq */
+  const double* C;   /* m_eq x n */
+  const double* d;   /* m_eq */
+  const double* l_x; /* n */
+  const double* u_x; /* n */
+  int ineq_bounds;   /* Settings::inequalities      (IPMZ_BOUNDS_*) */
+  int var_bounds;    /* Settings::variable_bounds   (IPMZ_BOUNDS_*) */
+  int equalities;    /* Settings::equalities */
+} ipmz_problem;
+
+typedef struct {
+  double tolerance;            /* 1e-8   Optimizer.cpp:124 */
+  int max_iter;                /* 100    Optimizer.cpp:125 */
+  double fraction_to_boundary; /* 0.995  Optimizer.cpp:216 */
+  double sigma_power;          /* 3      Optimizer.cpp:178 */
+  int reduction;               /* IPMZ_REDUCTION_* */
+  int device;                  /* CUDA device ordinal */
+  int record_steps;            /* keep every iteration's solved Newton steps for ipmz_get_trace */
+  int refine_steps;            /* normal reduction: iterative-refinement steps against the augmented
+                                  residual per Newton solve; -1 = default (1); ignored for AUGMENTED */
+} ipmz_options;
+
+typedef struct {
+  int iterations; /* Newton steps taken */
+  int converged;  /* 1 iff res < tol && mu < tol was met */
+  double f;       /* objective at the last evaluated iterate */
+  double res;     /* ||full Newton RHS at mu=0||_2  (Optimizer.cpp:240-247) */
+  double mu;      /* mean |complementarity|         (Optimizer.cpp:249-268) */
+  double solve_ms;        /* device time of the loop, CUDA events */
+  double factor_flops;    /* sum over iterations of N^3/3 */
+} ipmz_result;
+
+typedef struct ipmz_solver_s* ipmz_handle;
+typedef struct ipmz_batch_s* ipmz_batch_handle;
+typedef struct ipmz_factor_s* ipmz_factor_handle;
+
+const char* ipmz_last_error(void);
+const char* ipmz_version(void);
+int ipmz_device_count(void);
+void ipmz_default_options(ipmz_options* opt);
+int ipmz_iterate_len(const ipmz_problem* p);
+/* Page-locked host buffers for the end-to-end path (H2D / D2H at full PCIe rate). */
+void* ipmz_host_alloc(size_t bytes);
+void ipmz_host_free(void* p);
+/* Kernels launched by this library so far (bench.py reports the delta as gpu_launches). */
+unsigned long long ipmz_launch_count(void);
+/* FP64 tensor-pipe (DMMA) issue-rate ceiling of `device`, measured with a register-resident probe. */
+int ipmz_fp64_peak_probe(int device, double* tflops);
+
+/* ---- single QP, iterate device-resident across iterations ---- */
+int ipmz_create(const ipmz_problem* p, const ipmz_options* opt, ipmz_handle* out);
+int ipmz_destroy(ipmz_handle h);
+int ipmz_set_iterate(ipmz_handle h, const double* packed);
+int ipmz_get_iterate(ipmz_handle h, double* packed);
+int ipmz_reset_iterate(ipmz_handle h); /* the reference's initial point */
+int ipmz_solve(ipmz_handle h, ipmz_result* res);
+/* One predictor-corrector iteration at the current iterate WITHOUT moving it: writes the
+ * solved augmented steps [dx; dlam] (length n + m_ineq + m_eq) of the predictor and the
+ * corrector, as the reference prints them at Optimizer.cpp:359; any pointer may be NULL. */
+int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* alpha_aff,
+                     double* sigma, double* alpha);
+/* Per-iteration log of the last ipmz_solve: f/res/mu have iterations+1 entries (cap = how
+ * many the caller's arrays hold); steps need record_steps and hold cap x (n+m) doubles. */
+int ipmz_get_trace(ipmz_handle h, int cap, double* f, double* res, double* mu, double* step_aff,
+                   double* step_cor, double* alpha_aff, double* sigma, double* alpha);
+/* Dense copy (N x N, row-major, full symmetric) of the reduced matrix assembled at the
+ * current iterate, N = n+m (augmented) or n (normal). */
+int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out);
+
+/* ---- mirror of LinearSolvers (host buffers in/out, as the reference's free functions) ---- */
+/* L: n x n unit lower triangular (zeros above the diagonal), D: n pivots; a zero pivot is
+ * replaced by 1e-8 (LinearSolvers.cpp:28). */
+int ipmz_ldlt_decomposition(int n, const double* A, double* L, double* D);
+int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double* b);
+
+/* ---- device-resident factor + solve (bench / roofline path) ---- */
+int ipmz_factor_create(int n, int device, ipmz_factor_handle* out);
+int ipmz_factor_destroy(ipmz_factor_handle h);
+int ipmz_factor_set_matrix(ipmz_factor_handle h, const double* A_host); /* pristine copy kept */
+int ipmz_factor_set_rhs(ipmz_factor_handle h, const double* b_host);
+/* reps x { L,D <- LDL^T(pristine A) ; nrhs solves from the pristine rhs }, timed with CUDA
+ * events on the library stream; ms_total is the device time of all reps. */
+int ipmz_factor_run(ipmz_factor_handle h, int reps, int nrhs, double* ms_total);
+/* One factorization with CUDA events around every launch: ms3[0..2] = device time of the
+ * diagonal-block, panel and trailing-update (DMMA) kernels; flops_syrk / n_syrk = algorithmic
+ * flops and launch count of the trailing updates (the roofline numerator of bench.py). */
+int ipmz_factor_profile(ipmz_factor_handle h, double* ms3, double* flops_syrk, int* n_syrk);
+int ipmz_factor_get_solution(ipmz_factor_handle h, double* x_host);
+int ipmz_factor_get_ld(ipmz_factor_handle h, double* L_host, double* D_host);
+
+/* ---- batch of independent QPs with one shared shape/Settings (cfg4) ---- */
+/* Arrays hold `count` problems back to back (Q: count*n*n, A: count*m_ineq*n, ...). */
+int ipmz_batch_create(int count, const ipmz_problem* shape_and_data, const ipmz_options* opt,
+                      ipmz_batch_handle* out);
+int ipmz_batch_destroy(ipmz_batch_handle h);
+/* Upload (again) the problem data from host arrays laid out as at create; part of the
+ * end-to-end timed region of bench.py. */
+int ipmz_batch_upload(ipmz_batch_handle h, const ipmz_problem* data);
+int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem /* count entries or NULL */,
+                     double* ms_total);
+int ipmz_batch_get_iterates(ipmz_batch_handle h, double* packed /* count x iterate_len */);
+int ipmz_batch_get_x(ipmz_batch_handle h, double* x /* count x n */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

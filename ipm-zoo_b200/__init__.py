@@ -1,0 +1,14 @@
+"""ipm-zoo_b200 -- B200-native (sm_100a) numerical interior-point hot path of albfre/ipm-zoo.
+
+The product is the C-ABI shared library ``libipmz_b200.so`` (include/ipmz.h) built from
+``csrc/*.cu`` by ``build.sh``.  This Python package is only the ctypes binding used by
+tests/, bench.py and __graft_entry__.py; the reference-facing host layer is C++
+(``host/``).  There is no CPU fallback: importing works anywhere, but every compute call
+fails loudly without a CUDA device or without the built library.
+"""
+from .capi import (  # noqa: F401
+    AUGMENTED, NORMAL, NONE, LOWER, UPPER, BOTH,
+    IpmzError, Problem, Options, Result, Solver, BatchSolver, Factor,
+    ldlt_decomposition, overwriting_solve_ldlt, lib, lib_path, build, device_count, pinned_empty, launch_count, fp64_peak_tflops,
+    EXPORTED_SYMBOLS,
+)

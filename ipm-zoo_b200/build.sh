@@ -1,0 +1,17 @@
+#!/bin/sh
+# Builds ipm-zoo_b200/libipmz_b200.so for sm_100a (in-tree; the .so travels with gpurun).
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++"
+mkdir -p "$HERE/csrc/_obj"
+for f in vector_kernels assemble factor trsv solver linear_solvers; do
+  if [ ! -f "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/$f.cu" -nt "$HERE/csrc/_obj/$f.o" ] || \
+     [ "$HERE/csrc/ipmz_device.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ipmz_kernels.h" -nt "$HERE/csrc/_obj/$f.o" ] || \
+     [ "$HERE/../include/ipmz.h" -nt "$HERE/csrc/_obj/$f.o" ]; then
+    $NVCC $FLAGS ${VERBOSE:+-Xptxas -v} -c "$HERE/csrc/$f.cu" -o "$HERE/csrc/_obj/$f.o" &
+  fi
+done
+wait
+$NVCC -shared -ccbin /usr/bin/g++ -o "$HERE/libipmz_b200.so" "$HERE"/csrc/_obj/*.o -lcudart_static -ldl -lrt -lpthread
+echo "built $HERE/libipmz_b200.so"

@@ -1,0 +1,72 @@
+// ipm-zoo_b200/csrc/ipmz_kernels.h -- host-callable launchers of the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "ipmz_device.cuh"
+
+namespace ipmz {
+
+// every launcher bumps this (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+// ---- vector_kernels.cu ----
+void launch_matvec(cudaStream_t st, int nslots, const int* active, const double* A, int lda, size_t sA,
+                   int rows, int cols, const double* x, size_t sx, double* y, size_t sy);
+void launch_transpose(cudaStream_t st, int count, const double* M, int ldm, size_t sM, double* MT, int ldmt,
+                      size_t sMT, int m, int n);
+void launch_initial_point(cudaStream_t st, const View& v, int nslots);
+void launch_residuals_rhs(cudaStream_t st, const View& v, int nslots, int mode);
+void launch_prepare_sol(cudaStream_t st, const View& v, int nslots, const double* rvec, int stage);
+void launch_recover_dual(cudaStream_t st, const View& v, int nslots, const double* rvec, int accumulate);
+void launch_aug_residual(cudaStream_t st, const View& v, int nslots);
+void launch_backsub_step(cudaStream_t st, const View& v, int nslots, int mode);
+void launch_mu_affine(cudaStream_t st, const View& v, int nslots);
+void launch_update(cudaStream_t st, const View& v, int nslots);
+
+// ---- assemble.cu ----
+// Augmented KKT [[Q + Y^-1 L_y + Z^-1 L_z, M^T],[M, -W^-1]] (full symmetric, N = n+m) or the
+// diagonal-shifted copy Q + Y^-1 L_y + Z^-1 L_z that the condensed assembly accumulates
+// M^T W M onto (N = n).
+void launch_assemble(cudaStream_t st, const View& v, int nslots);
+
+// ---- factor.cu ----
+struct FactorPlan {
+  int N;        // matrix dimension
+  int ld;       // leading dimension (multiple of 4)
+  size_t sK;    // per-problem stride of the matrix
+  size_t sD;    // per-problem stride of the pivots
+  int nslots;   // problems in this launch
+  const int* active;
+};
+int factor_init();  // opt-in shared memory sizes; returns cudaError_t
+// L, Dg <- LDL^T(src).  src == dst factors in place; otherwise the first panel step reads src
+// and writes dst so no separate copy pass is needed (the reference's ldlt_decomposition is
+// out-of-place, LinearSolvers.cpp:14-42).
+void launch_ldlt(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg);
+// Same, with CUDA events around every launch; ms[0..2] += device time of the diagonal-block,
+// panel and trailing-update (DMMA) kernels; flops_syrk += algorithmic flops of the updates.
+int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
+                         double ms[3], double* flops_syrk, int* n_syrk);
+// Register-resident DMMA issue-rate probe: the FP64 tensor-pipe ceiling of this device.
+int fp64_peak_probe(cudaStream_t st, double* tflops);
+// C (rows x rows, lower triangle) += sign * P diag(d) P^T with P rows x kdim; the DMMA kernel
+// shared by the trailing update of the factorization (sign -1, P = the panel of L, d = pivots)
+// and the condensed assembly M^T W M (sign +1, P = MT, d = W).
+void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
+                     size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
+                     int kdim, double sign);
+
+// ---- trsv.cu ----
+struct TrsvWork {
+  int* flags;      // [nslots][nblk]
+  int* ticket;     // [1]
+  int epoch;       // bumped by every launch
+  int cap_blocks;  // flags capacity per slot
+};
+// x <- L^-1 x (unit lower), then x <- L^-T D^-1 x; L strict-lower of K, in place on x.
+void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, const double* Dg, double* x,
+                       size_t sx, TrsvWork& w);
+
+}  // namespace ipmz

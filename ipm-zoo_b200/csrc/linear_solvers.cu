@@ -1,0 +1,222 @@
+// ipm-zoo_b200/csrc/linear_solvers.cu -- C ABI mirror of NumericalOptimization::LinearSolvers
+// (include/NumericalOptimization/LinearSolvers.h:11-17) on host buffers, and the
+// device-resident factor+solve object that bench.py times against the FP64 roofline.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ipmz.h"
+#include "ipmz_device.cuh"
+#include "ipmz_kernels.h"
+
+namespace ipmz {
+int ipmz_fail(int code, const std::string& msg);
+int ipmz_ensure_device(int device);
+}  // namespace ipmz
+using namespace ipmz;
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return ipmz_fail(IPMZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+struct ipmz_factor_s {
+  int device = 0, n = 0, ld = 0;
+  double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr;
+  TrsvWork tw{};
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+static FactorPlan plan(const ipmz_factor_s* h) {
+  FactorPlan fp;
+  fp.N = h->n; fp.ld = h->ld; fp.sK = (size_t)h->n * h->ld; fp.sD = (size_t)h->ld; fp.nslots = 1; fp.active = nullptr;
+  return fp;
+}
+
+extern "C" {
+
+int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
+  if (!out || n <= 0) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(device))) return rc;
+  ipmz_factor_s* h = new ipmz_factor_s();
+  h->device = device; h->n = n; h->ld = pad4(n);
+  const size_t bytes = sizeof(double) * (size_t)n * h->ld;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&h->A, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->L, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->Dg, sizeof(double) * h->ld);
+  if (e == cudaSuccess) e = cudaMalloc(&h->b, sizeof(double) * h->ld);
+  if (e == cudaSuccess) e = cudaMalloc(&h->x, sizeof(double) * h->ld);
+  h->tw.cap_blocks = (n + 63) / 64;
+  if (e == cudaSuccess) e = cudaMalloc(&h->tw.flags, sizeof(int) * h->tw.cap_blocks);
+  if (e == cudaSuccess) e = cudaMalloc(&h->tw.ticket, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->A, 0, bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->L, 0, bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->b, 0, sizeof(double) * h->ld);
+  if (e == cudaSuccess) e = cudaMemset(h->x, 0, sizeof(double) * h->ld);
+  if (e == cudaSuccess) e = cudaMemset(h->tw.flags, 0, sizeof(int) * h->tw.cap_blocks);
+  if (e == cudaSuccess) e = cudaMemset(h->tw.ticket, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->e1);
+  if (e != cudaSuccess) {
+    ipmz_factor_destroy(h);
+    return ipmz_fail(IPMZ_ERR_ALLOC, std::string("factor_create: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return IPMZ_OK;
+}
+
+int ipmz_factor_destroy(ipmz_factor_handle h) {
+  if (!h) return IPMZ_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x);
+  cudaFree(h->tw.flags); cudaFree(h->tw.ticket);
+  if (h->e0) cudaEventDestroy(h->e0);
+  if (h->e1) cudaEventDestroy(h->e1);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return IPMZ_OK;
+}
+
+int ipmz_factor_set_matrix(ipmz_factor_handle h, const double* A_host) {
+  if (!h || !A_host) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  CUDA_TRY(cudaMemcpy2D(h->A, sizeof(double) * h->ld, A_host, sizeof(double) * h->n, sizeof(double) * h->n, h->n,
+                        cudaMemcpyHostToDevice));
+  return IPMZ_OK;
+}
+
+int ipmz_factor_set_rhs(ipmz_factor_handle h, const double* b_host) {
+  if (!h || !b_host) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  CUDA_TRY(cudaMemcpy(h->b, b_host, sizeof(double) * h->n, cudaMemcpyHostToDevice));
+  return IPMZ_OK;
+}
+
+int ipmz_factor_run(ipmz_factor_handle h, int reps, int nrhs, double* ms_total) {
+  if (!h || reps <= 0 || nrhs < 0) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  const FactorPlan fp = plan(h);
+  CUDA_TRY(cudaEventRecord(h->e0, h->st));
+  for (int r = 0; r < reps; ++r) {
+    launch_ldlt(h->st, fp, h->A, h->L, h->Dg);
+    for (int k = 0; k < nrhs; ++k) {
+      CUDA_TRY(cudaMemcpyAsync(h->x, h->b, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->st));
+      launch_ldlt_solve(h->st, fp, h->L, h->Dg, h->x, (size_t)h->ld, h->tw);
+    }
+  }
+  CUDA_TRY(cudaEventRecord(h->e1, h->st));
+  CUDA_TRY(cudaEventSynchronize(h->e1));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->e0, h->e1));
+  if (ms_total) *ms_total = ms;
+  return IPMZ_OK;
+}
+
+// One profiled factorization: ms[0..2] = device time of the diagonal-block, panel and
+// trailing-update kernels (CUDA events around each launch on the library stream),
+// flops_syrk = algorithmic flops of the trailing updates, n_syrk = their launch count.
+int ipmz_factor_profile(ipmz_factor_handle h, double* ms3, double* flops_syrk, int* n_syrk) {
+  if (!h || !ms3) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  ms3[0] = ms3[1] = ms3[2] = 0.0;
+  if (flops_syrk) *flops_syrk = 0.0;
+  if (n_syrk) *n_syrk = 0;
+  const FactorPlan fp = plan(h);
+  const int e = launch_ldlt_profiled(h->st, fp, h->A, h->L, h->Dg, ms3, flops_syrk, n_syrk);
+  if (e != 0) return ipmz_fail(IPMZ_ERR_CUDA, std::string("factor_profile: ") + cudaGetErrorString((cudaError_t)e));
+  return IPMZ_OK;
+}
+
+int ipmz_fp64_peak_probe(int device, double* tflops) {
+  if (!tflops) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(device))) return rc;
+  const int e = fp64_peak_probe(0, tflops);
+  if (e != 0) return ipmz_fail(IPMZ_ERR_CUDA, std::string("fp64_peak_probe: ") + cudaGetErrorString((cudaError_t)e));
+  return IPMZ_OK;
+}
+
+int ipmz_factor_get_solution(ipmz_factor_handle h, double* x_host) {
+  if (!h || !x_host) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  CUDA_TRY(cudaMemcpy(x_host, h->x, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+  return IPMZ_OK;
+}
+
+// L in the reference's format: unit diagonal, zeros above (LinearSolvers.cpp:18,38).
+int ipmz_factor_get_ld(ipmz_factor_handle h, double* L_host, double* D_host) {
+  if (!h) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(h->device))) return rc;
+  const int n = h->n;
+  if (L_host) {
+    CUDA_TRY(cudaMemcpy2D(L_host, sizeof(double) * n, h->L, sizeof(double) * h->ld, sizeof(double) * n, n,
+                          cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      L_host[(size_t)i * n + i] = 1.0;
+      for (int j = i + 1; j < n; ++j) L_host[(size_t)i * n + j] = 0.0;
+    }
+  }
+  if (D_host) CUDA_TRY(cudaMemcpy(D_host, h->Dg, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return IPMZ_OK;
+}
+
+int ipmz_ldlt_decomposition(int n, const double* A, double* L, double* D) {
+  if (n < 0 || (n > 0 && (!A || !L || !D))) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  if (n == 0) return IPMZ_OK;
+  ipmz_factor_handle h = nullptr;
+  int rc = ipmz_factor_create(n, 0, &h);
+  if (rc) return rc;
+  rc = ipmz_factor_set_matrix(h, A);
+  double ms;
+  if (!rc) rc = ipmz_factor_run(h, 1, 0, &ms);
+  if (!rc) rc = ipmz_factor_get_ld(h, L, D);
+  ipmz_factor_destroy(h);
+  return rc;
+}
+
+int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double* b) {
+  if (n < 0 || (n > 0 && (!L || !D || !b))) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  if (n == 0) return IPMZ_OK;  // LinearSolvers.cpp:46-48
+  ipmz_factor_handle h = nullptr;
+  int rc = ipmz_factor_create(n, 0, &h);
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpy2D(h->L, sizeof(double) * h->ld, L, sizeof(double) * n, sizeof(double) * n, n,
+                               cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->Dg, D, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->x, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const FactorPlan fp = plan(h);
+    launch_ldlt_solve(h->st, fp, h->L, h->Dg, h->x, (size_t)h->ld, h->tw);
+    e = cudaStreamSynchronize(h->st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(b, h->x, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  ipmz_factor_destroy(h);
+  if (e != cudaSuccess) return ipmz_fail(IPMZ_ERR_CUDA, std::string("solve_ldlt: ") + cudaGetErrorString(e));
+  return IPMZ_OK;
+}
+
+void* ipmz_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void ipmz_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,695 @@
+// ipm-zoo_b200/csrc/solver.cu -- host driver of the device-resident Mehrotra
+// predictor-corrector loop and the C ABI of include/ipmz.h.
+//
+// Reference control flow: Optimizer::solve_quasi_definite_ (Optimizer.cpp:77-220).  The
+// iterate, slacks, duals, residuals and directions stay in HBM for the whole solve; per
+// iteration the host reads back one small Scal record per problem (f, res, mu, done) to run
+// the reference's stopping test and to maintain the list of still-active problems of a batch.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ipmz.h"
+#include "ipmz_device.cuh"
+#include "ipmz_kernels.h"
+
+namespace ipmz {
+
+unsigned long long g_launch_count = 0;
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int ipmz_fail(int code, const std::string& msg) { return fail(code, msg); }
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(IPMZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+  } while (0)
+
+static bool g_factor_init_done[64] = {false};
+
+static int ensure_device(int device) {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0)
+    return fail(IPMZ_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  if (device < 0 || device >= cnt) return fail(IPMZ_ERR_ARG, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  if (device < 64 && !g_factor_init_done[device]) {
+    const int rc = factor_init();
+    if (rc != 0) return fail(IPMZ_ERR_CUDA, std::string("factor_init: ") + cudaGetErrorString((cudaError_t)rc));
+    g_factor_init_done[device] = true;
+  }
+  return IPMZ_OK;
+}
+
+int ipmz_ensure_device(int device) { return ensure_device(device); }
+
+template <class T>
+static int dalloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) return fail(IPMZ_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(*p, 0, count * sizeof(T));
+  if (e != cudaSuccess) return fail(IPMZ_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  return IPMZ_OK;
+}
+
+// Everything one batch of `count` equally-shaped QPs needs on the device.
+struct Workspace {
+  int device = 0, count = 0;
+  ipmz_options opt{};
+  View v{};
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void*> allocs;
+  double *Q = nullptr, *M = nullptr, *MT = nullptr, *c = nullptr, *lx = nullptr, *ux = nullptr, *lo = nullptr,
+         *up = nullptr;
+  int* active_dev = nullptr;
+  TrsvWork tw{};
+  int Naug = 0;
+  int refine = 0;  // iterative-refinement steps of the normal reduction
+  // host mirrors
+  std::vector<Scal> sc_host;
+  std::vector<int> active_host;
+  // trace of the last solve (single-problem handles)
+  std::vector<double> tr_f, tr_res, tr_mu, tr_alpha_aff, tr_sigma, tr_alpha;
+  double* steps_dev = nullptr;  // [max_iter][2][Naug] when record_steps
+  int tr_iters = 0;
+  bool iterate_set = false;
+
+  ~Workspace() {
+    cudaSetDevice(device);
+    for (void* p : allocs) cudaFree(p);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (st) cudaStreamDestroy(st);
+  }
+  template <class T>
+  int alloc(T** p, size_t n) {
+    const int rc = dalloc(p, n);
+    if (rc == IPMZ_OK) allocs.push_back(*p);
+    return rc;
+  }
+};
+
+static int check_problem(const ipmz_problem* p) {
+  if (!p) return fail(IPMZ_ERR_ARG, "null problem");
+  if (p->n <= 0) return fail(IPMZ_ERR_ARG, "n must be positive");
+  if (p->m_ineq < 0 || p->m_eq < 0) return fail(IPMZ_ERR_ARG, "negative row count");
+  if (!p->Q || !p->c || !p->l_x || !p->u_x) return fail(IPMZ_ERR_ARG, "Q, c, l_x, u_x are required");
+  const bool ineq = p->ineq_bounds != IPMZ_BOUNDS_NONE && p->m_ineq > 0;
+  const bool eq = p->equalities && p->m_eq > 0;
+  if (ineq && (!p->A || !p->l_A || !p->u_A)) return fail(IPMZ_ERR_ARG, "A, l_A, u_A are required");
+  if (eq && (!p->C || !p->d)) return fail(IPMZ_ERR_ARG, "C, d are required");
+  if (p->ineq_bounds < 0 || p->ineq_bounds > 3 || p->var_bounds < 0 || p->var_bounds > 3)
+    return fail(IPMZ_ERR_ARG, "bounds selector out of range");
+  return IPMZ_OK;
+}
+
+static void fill_shape(Shape& s, const ipmz_problem* p) {
+  const bool ineq = p->ineq_bounds != IPMZ_BOUNDS_NONE && p->m_ineq > 0;
+  const bool eq = p->equalities && p->m_eq > 0;
+  s.n = p->n;
+  s.mi = ineq ? p->m_ineq : 0;
+  s.m = s.mi + (eq ? p->m_eq : 0);
+  s.ns = pad4(s.n);
+  s.ms = pad4(s.m);
+  s.ylo = (p->var_bounds == IPMZ_BOUNDS_LOWER || p->var_bounds == IPMZ_BOUNDS_BOTH);
+  s.zup = (p->var_bounds == IPMZ_BOUNDS_UPPER || p->var_bounds == IPMZ_BOUNDS_BOTH);
+  s.ilo = ineq && (p->ineq_bounds == IPMZ_BOUNDS_LOWER || p->ineq_bounds == IPMZ_BOUNDS_BOTH);
+  s.iup = ineq && (p->ineq_bounds == IPMZ_BOUNDS_UPPER || p->ineq_bounds == IPMZ_BOUNDS_BOTH);
+  s.clamp_x = ineq ? 0 : 1;
+  s.ncomp = (s.ilo + s.iup) * s.mi + 2 * (s.m - s.mi) + (s.ylo + s.zup) * s.n;
+}
+
+// host [rows x cols] dense (count blocks back to back) -> device pitched rows
+static int upload_pitched(double* dst, int ld, const double* src, int cols, size_t rows, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return IPMZ_OK;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), src, (size_t)cols * sizeof(double),
+                             (size_t)cols * sizeof(double), rows, cudaMemcpyHostToDevice, st));
+  return IPMZ_OK;
+}
+
+static int upload_data(Workspace& w, const ipmz_problem* p) {
+  const Shape& s = w.v.s;
+  const int count = w.count;
+  const int me = s.m - s.mi;
+  int rc;
+  // the reference's bound checks (EnvironmentBuilder.cpp:10-17)
+  for (size_t i = 0; i < (size_t)count * s.n; ++i)
+    if (!(p->l_x[i] < p->u_x[i])) return fail(IPMZ_ERR_BOUNDS, "l_x < u_x violated");
+  for (size_t i = 0; i < (size_t)count * s.mi; ++i)
+    if (!(p->l_A[i] <= p->u_A[i])) return fail(IPMZ_ERR_BOUNDS, "l_A <= u_A violated");
+  if ((rc = upload_pitched(w.Q, w.v.ldq, p->Q, s.n, (size_t)count * s.n, w.st))) return rc;
+  if ((rc = upload_pitched(w.c, s.ns, p->c, s.n, count, w.st))) return rc;
+  if ((rc = upload_pitched(w.lx, s.ns, p->l_x, s.n, count, w.st))) return rc;
+  if ((rc = upload_pitched(w.ux, s.ns, p->u_x, s.n, count, w.st))) return rc;
+  if (s.m > 0) {
+    if (s.mi > 0 && me == 0) {
+      if ((rc = upload_pitched(w.M, w.v.ldm, p->A, s.n, (size_t)count * s.mi, w.st))) return rc;
+      if ((rc = upload_pitched(w.lo, s.ms, p->l_A, s.mi, count, w.st))) return rc;
+      if ((rc = upload_pitched(w.up, s.ms, p->u_A, s.mi, count, w.st))) return rc;
+    } else if (s.mi == 0) {
+      if ((rc = upload_pitched(w.M, w.v.ldm, p->C, s.n, (size_t)count * me, w.st))) return rc;
+      if ((rc = upload_pitched(w.lo, s.ms, p->d, me, count, w.st))) return rc;
+      if ((rc = upload_pitched(w.up, s.ms, p->d, me, count, w.st))) return rc;
+    } else {
+      for (int q = 0; q < count; ++q) {
+        double* Mq = w.M + (size_t)q * w.v.sM;
+        if ((rc = upload_pitched(Mq, w.v.ldm, p->A + (size_t)q * s.mi * s.n, s.n, s.mi, w.st))) return rc;
+        if ((rc = upload_pitched(Mq + (size_t)s.mi * w.v.ldm, w.v.ldm, p->C + (size_t)q * me * s.n, s.n, me, w.st)))
+          return rc;
+        CUDA_TRY(cudaMemcpyAsync(w.lo + (size_t)q * s.ms, p->l_A + (size_t)q * s.mi, sizeof(double) * s.mi,
+                                 cudaMemcpyHostToDevice, w.st));
+        CUDA_TRY(cudaMemcpyAsync(w.up + (size_t)q * s.ms, p->u_A + (size_t)q * s.mi, sizeof(double) * s.mi,
+                                 cudaMemcpyHostToDevice, w.st));
+        CUDA_TRY(cudaMemcpyAsync(w.lo + (size_t)q * s.ms + s.mi, p->d + (size_t)q * me, sizeof(double) * me,
+                                 cudaMemcpyHostToDevice, w.st));
+        CUDA_TRY(cudaMemcpyAsync(w.up + (size_t)q * s.ms + s.mi, p->d + (size_t)q * me, sizeof(double) * me,
+                                 cudaMemcpyHostToDevice, w.st));
+      }
+    }
+    launch_transpose(w.st, count, w.M, w.v.ldm, w.v.sM, w.MT, w.v.ldmt, w.v.sMT, s.m, s.n);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return IPMZ_OK;
+}
+
+static int create_workspace(Workspace** out, int count, const ipmz_problem* p, const ipmz_options* opt_in) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (count <= 0) return fail(IPMZ_ERR_ARG, "count must be positive");
+  ipmz_options opt;
+  if (opt_in) opt = *opt_in; else ipmz_default_options(&opt);
+  if (opt.reduction != IPMZ_REDUCTION_AUGMENTED && opt.reduction != IPMZ_REDUCTION_NORMAL)
+    return fail(IPMZ_ERR_ARG, "unknown reduction");
+  if ((rc = ensure_device(opt.device))) return rc;
+
+  Workspace* w = new Workspace();
+  std::unique_ptr<Workspace> guard(w);
+  w->device = opt.device;
+  w->count = count;
+  w->opt = opt;
+  View& v = w->v;
+  fill_shape(v.s, p);
+  const Shape& s = v.s;
+  // EqualityHandling::None would put a symbolic zero on the diagonal of the augmented system:
+  // the reference routes that to solve_indefinite_() == ASSERT(false) (Optimizer.cpp:63-75).
+  if (p->m_eq > 0 && !p->equalities)
+    return fail(IPMZ_ERR_INDEFINITE, "equality rows given but Settings::equalities is off");
+  w->Naug = s.n + s.m;
+  v.normal = (opt.reduction == IPMZ_REDUCTION_NORMAL) ? 1 : 0;
+  v.N = v.normal ? s.n : w->Naug;
+  v.ldk = pad4(v.N);
+  v.sK = (size_t)v.N * v.ldk;
+  v.ldq = s.ns; v.ldm = s.ns; v.ldmt = s.ms;
+  v.sQ = (size_t)s.n * s.ns; v.sM = (size_t)s.m * s.ns; v.sMT = (size_t)s.n * s.ms;
+  v.sp = (size_t)N_NSLOTS * s.ns + (size_t)N_MSLOTS * s.ms;
+  v.ssol = pad4(w->Naug);
+  v.tol = opt.tolerance; v.ftb = opt.fraction_to_boundary; v.sigma_pow = opt.sigma_power;
+  v.max_iter = opt.max_iter;
+  w->refine = v.normal ? (opt.refine_steps < 0 ? 1 : opt.refine_steps) : 0;
+  const int len = std::max(s.ns, s.ms);
+  v.maxblk = (len + 255) / 256;
+
+  CUDA_TRY(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&w->ev0));
+  CUDA_TRY(cudaEventCreate(&w->ev1));
+  const size_t C = (size_t)count;
+#define ALLOC(ptr, n) if ((rc = w->alloc(&(ptr), (n)))) return rc
+  ALLOC(w->Q, C * v.sQ); ALLOC(w->M, C * v.sM); ALLOC(w->MT, C * v.sMT);
+  ALLOC(w->c, C * s.ns); ALLOC(w->lx, C * s.ns); ALLOC(w->ux, C * s.ns);
+  ALLOC(w->lo, C * s.ms); ALLOC(w->up, C * s.ms);
+  ALLOC(v.V, C * v.sp); ALLOC(v.D, C * v.sp); ALLOC(v.DA, C * v.sp); ALLOC(v.R, C * v.sp);
+  ALLOC(v.Qx, C * s.ns); ALLOC(v.MTl, C * s.ns); ALLOC(v.tn, C * s.ns);
+  ALLOC(v.Mx, C * s.ms); ALLOC(v.winv, C * s.ms); ALLOC(v.W, C * s.ms); ALLOC(v.tm, C * s.ms);
+  ALLOC(v.rhs, C * (s.ns + s.ms)); ALLOC(v.sol, C * v.ssol);
+  ALLOC(v.out, C * (s.ns + s.ms)); ALLOC(v.resid, C * (s.ns + s.ms)); ALLOC(v.Qd, C * s.ns);
+  ALLOC(v.K, C * v.sK); ALLOC(v.Dg, C * v.ldk);
+  ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
+  ALLOC(w->active_dev, C);
+  w->tw.cap_blocks = (v.N + 63) / 64;
+  ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
+  if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
+#undef ALLOC
+  v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
+  v.active = nullptr;
+  w->sc_host.resize(count);
+  w->active_host.resize(count);
+
+  if ((rc = upload_data(*w, p))) return rc;
+  launch_initial_point(w->st, v, count);
+  CUDA_TRY(cudaStreamSynchronize(w->st));
+  CUDA_TRY(cudaGetLastError());
+  guard.release();
+  *out = w;
+  return IPMZ_OK;
+}
+
+static FactorPlan plan_of(const Workspace& w, int nslots, const int* active) {
+  FactorPlan fp;
+  fp.N = w.v.N; fp.ld = w.v.ldk; fp.sK = w.v.sK; fp.sD = (size_t)w.v.ldk; fp.nslots = nslots; fp.active = active;
+  return fp;
+}
+
+// matvecs that open an iteration: Q x, M x, M^T lambda
+static void iteration_matvecs(Workspace& w, const View& v, int nslots) {
+  const Shape& s = v.s;
+  launch_matvec(w.st, nslots, v.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.V /* x slot 0 */, v.sp, v.Qx, s.ns);
+  if (s.m > 0) {
+    launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.V, v.sp, v.Mx, s.ms);
+    launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m,
+                  v.V + (size_t)N_NSLOTS * s.ns /* lam slot */, v.sp, v.MTl, s.ns);
+  }
+}
+
+static void assemble_and_factor(Workspace& w, const View& v, int nslots) {
+  const Shape& s = v.s;
+  launch_assemble(w.st, v, nslots);
+  if (v.normal && s.m > 0)
+    launch_syrk_ldl(w.st, nslots, v.active, v.K, v.K, v.ldk, v.sK, v.MT, v.ldmt, v.sMT, v.W, s.ms, s.n, s.m, 1.0);
+}
+
+// Normal reduction: condensed solve of the augmented right-hand side rvec = b0|b1,
+//   (Hx + M^T W M) dx = b0 + M^T W b1,   dlam = W (M dx - b1),   out (+)= [dx; dlam].
+static void condensed_solve(Workspace& w, const View& v, int nslots, const double* rvec, int accumulate) {
+  const Shape& s = v.s;
+  const FactorPlan fp = plan_of(w, nslots, v.active);
+  if (s.m > 0) {
+    launch_prepare_sol(w.st, v, nslots, rvec, 0);
+    launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.tm, s.ms, v.tn, s.ns);
+  }
+  launch_prepare_sol(w.st, v, nslots, rvec, 1);
+  launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
+  if (s.m > 0) launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.sol, v.ssol, v.Mx, s.ms);
+  launch_recover_dual(w.st, v, nslots, rvec, accumulate);
+}
+
+// one Newton solve with the current factor: rhs -> direction (mode 0: affine, 1: corrector)
+static void newton_direction(Workspace& w, const View& v, int nslots, int mode) {
+  const Shape& s = v.s;
+  if (!v.normal) {
+    const FactorPlan fp = plan_of(w, nslots, v.active);
+    launch_prepare_sol(w.st, v, nslots, v.rhs, 0);
+    launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
+  } else {
+    condensed_solve(w, v, nslots, v.rhs, 0);
+    for (int r = 0; r < w.refine; ++r) {
+      const size_t so = (size_t)s.ns + s.ms;
+      launch_matvec(w.st, nslots, v.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.out, so, v.Qd, s.ns);
+      if (s.m > 0) {
+        launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.out + s.ns, so, v.tn, s.ns);
+        launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.out, so, v.Mx, s.ms);
+      }
+      launch_aug_residual(w.st, v, nslots);
+      condensed_solve(w, v, nslots, v.resid, 1);
+    }
+  }
+  launch_backsub_step(w.st, v, nslots, mode);
+}
+
+static void newton_iteration(Workspace& w, const View& v, int nslots, bool update, int record_iter) {
+  assemble_and_factor(w, v, nslots);
+  const FactorPlan fp = plan_of(w, nslots, v.active);
+  launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
+  newton_direction(w, v, nslots, 0);
+  launch_mu_affine(w.st, v, nslots);
+  launch_residuals_rhs(w.st, v, nslots, 1);
+  newton_direction(w, v, nslots, 1);
+  if (record_iter >= 0 && w.steps_dev) {
+    const Shape& s = v.s;
+    double* dst = w.steps_dev + (size_t)record_iter * 2 * w.Naug;
+    const double* packs[2] = {v.DA, v.D};
+    for (int k = 0; k < 2; ++k) {
+      cudaMemcpyAsync(dst + (size_t)k * w.Naug, packs[k], sizeof(double) * s.n, cudaMemcpyDeviceToDevice, w.st);
+      if (s.m > 0)
+        cudaMemcpyAsync(dst + (size_t)k * w.Naug + s.n, packs[k] + (size_t)N_NSLOTS * s.ns, sizeof(double) * s.m,
+                        cudaMemcpyDeviceToDevice, w.st);
+    }
+  }
+  if (update) launch_update(w.st, v, nslots);
+}
+
+static int run_ipm(Workspace& w, double* ms_out) {
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  const int count = w.count;
+  View v = w.v;
+  w.tr_f.clear(); w.tr_res.clear(); w.tr_mu.clear();
+  w.tr_alpha_aff.clear(); w.tr_sigma.clear(); w.tr_alpha.clear();
+  int nact = count;
+  for (int i = 0; i < count; ++i) w.active_host[i] = i;
+  bool identity = true;
+  CUDA_TRY(cudaEventRecord(w.ev0, w.st));
+  int it = 0;
+  for (;; ++it) {
+    v.active = identity ? nullptr : w.active_dev;
+    iteration_matvecs(w, v, nact);
+    launch_residuals_rhs(w.st, v, nact, 0);
+    CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal) * count, cudaMemcpyDeviceToHost, w.st));
+    CUDA_TRY(cudaStreamSynchronize(w.st));
+    if (count == 1) {
+      const Scal& sc = w.sc_host[0];
+      if (it > 0) { w.tr_alpha_aff.push_back(sc.alpha_aff); w.tr_sigma.push_back(sc.sigma); w.tr_alpha.push_back(sc.alpha); }
+      w.tr_f.push_back(sc.f); w.tr_res.push_back(sc.res); w.tr_mu.push_back(sc.mu);
+    }
+    int na = 0;
+    for (int i = 0; i < nact; ++i) {
+      const int q = w.active_host[i];
+      if (w.sc_host[q].done == 0) w.active_host[na++] = q;
+    }
+    if (na != nact) {
+      nact = na;
+      identity = false;
+      if (nact > 0)
+        CUDA_TRY(cudaMemcpyAsync(w.active_dev, w.active_host.data(), sizeof(int) * nact, cudaMemcpyHostToDevice, w.st));
+    }
+    if (nact == 0) break;
+    v.active = identity ? nullptr : w.active_dev;
+    newton_iteration(w, v, nact, true, (count == 1 && w.opt.record_steps) ? it : -1);
+  }
+  CUDA_TRY(cudaEventRecord(w.ev1, w.st));
+  CUDA_TRY(cudaEventSynchronize(w.ev1));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+  if (ms_out) *ms_out = ms;
+  w.tr_iters = it;
+  return IPMZ_OK;
+}
+
+static void fill_result(const Workspace& w, int q, ipmz_result* r, double ms) {
+  const Scal& sc = w.sc_host[q];
+  r->iterations = sc.iters;
+  r->converged = sc.done == 1 ? 1 : 0;
+  r->f = sc.f; r->res = sc.res; r->mu = sc.mu;
+  r->solve_ms = ms;
+  const double N = (double)w.v.N;
+  r->factor_flops = (double)sc.iters * N * N * N / 3.0;
+}
+
+// ---- packed iterate <-> device packs -------------------------------------------------
+// device slot order: n-slots X LAMY LAMZ Y Z ; m-slots LAM SV LAML LAMU SL SU (stacked ineq|eq)
+struct HostLayout {
+  int n, mi_host, me_host;  // sizes of the caller's packed iterate
+  size_t off_x, off_ineq, off_eq, off_lamy, off_lamz, off_y, off_z, len;
+};
+
+static HostLayout host_layout(int n, int mi_host, int me_host) {
+  HostLayout h;
+  h.n = n; h.mi_host = mi_host; h.me_host = me_host;
+  h.off_x = 0;
+  h.off_ineq = n;
+  h.off_eq = h.off_ineq + (size_t)6 * mi_host;
+  h.off_lamy = h.off_eq + (size_t)6 * me_host;
+  h.off_lamz = h.off_lamy + n;
+  h.off_y = h.off_lamz + n;
+  h.off_z = h.off_y + n;
+  h.len = h.off_z + n;
+  return h;
+}
+
+}  // namespace ipmz
+
+// =========================================================================================
+using namespace ipmz;
+
+struct ipmz_solver_s {
+  Workspace* w;
+  int mi_host, me_host;  // row counts of the caller's ipmz_problem (packed iterate sizing)
+};
+struct ipmz_batch_s {
+  Workspace* w;
+  int mi_host, me_host;
+  double last_ms;
+};
+
+extern "C" {
+
+const char* ipmz_last_error(void) { return g_err.c_str(); }
+const char* ipmz_version(void) { return "ipm-zoo_b200 0.1 (sm_100a)"; }
+
+int ipmz_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+
+void ipmz_default_options(ipmz_options* opt) {
+  opt->tolerance = 1e-8;
+  opt->max_iter = 100;
+  opt->fraction_to_boundary = 0.995;
+  opt->sigma_power = 3.0;
+  opt->reduction = IPMZ_REDUCTION_AUGMENTED;
+  opt->device = 0;
+  opt->record_steps = 0;
+  opt->refine_steps = -1;
+}
+
+unsigned long long ipmz_launch_count(void) { return g_launch_count; }
+
+int ipmz_iterate_len(const ipmz_problem* p) { return 5 * p->n + 6 * p->m_ineq + 6 * p->m_eq; }
+
+// Copy between the caller's packed iterate(s) and the device packs. dir 0: host->device.
+static int move_iterates(Workspace& w, int mi_host, int me_host, double* packed, int dir) {
+  const Shape& s = w.v.s;
+  const int n = s.n, me_dev = s.m - s.mi;
+  const HostLayout h = host_layout(n, mi_host, me_host);
+  const size_t C = (size_t)w.count;
+  std::vector<double> dev(C * w.v.sp, 0.0);
+  if (ensure_device(w.device)) return IPMZ_ERR_CUDA;
+  // start from the current device contents so untouched padding / absent groups survive
+  CUDA_TRY(cudaMemcpy(dev.data(), w.v.V, sizeof(double) * dev.size(), cudaMemcpyDeviceToHost));
+  for (size_t q = 0; q < C; ++q) {
+    double* hp = packed + q * h.len;
+    double* dp = dev.data() + q * w.v.sp;
+    auto mv = [&](double* hptr, double* dptr, int len) {
+      if (len <= 0) return;
+      if (dir == 0) std::memcpy(dptr, hptr, sizeof(double) * len);
+      else std::memcpy(hptr, dptr, sizeof(double) * len);
+    };
+    mv(hp + h.off_x, dp + (size_t)X * s.ns, n);
+    mv(hp + h.off_lamy, dp + (size_t)LAMY * s.ns, n);
+    mv(hp + h.off_lamz, dp + (size_t)LAMZ * s.ns, n);
+    mv(hp + h.off_y, dp + (size_t)YS * s.ns, n);
+    mv(hp + h.off_z, dp + (size_t)ZS * s.ns, n);
+    // host m-group order: lam, s, lam_lower, lam_upper, slack_lower, slack_upper == device order
+    double* dm = dp + (size_t)N_NSLOTS * s.ns;
+    for (int k = 0; k < N_MSLOTS; ++k) {
+      if (s.mi > 0) mv(hp + h.off_ineq + (size_t)k * mi_host, dm + (size_t)k * s.ms, s.mi);
+      if (me_dev > 0) mv(hp + h.off_eq + (size_t)k * me_host, dm + (size_t)k * s.ms + s.mi, me_dev);
+    }
+  }
+  if (dir == 0) CUDA_TRY(cudaMemcpy(w.v.V, dev.data(), sizeof(double) * dev.size(), cudaMemcpyHostToDevice));
+  return IPMZ_OK;
+}
+
+int ipmz_create(const ipmz_problem* p, const ipmz_options* opt, ipmz_handle* out) {
+  if (!out) return fail(IPMZ_ERR_ARG, "null out handle");
+  Workspace* w = nullptr;
+  const int rc = create_workspace(&w, 1, p, opt);
+  if (rc) return rc;
+  *out = new ipmz_solver_s{w, p->m_ineq, p->m_eq};
+  return IPMZ_OK;
+}
+
+int ipmz_destroy(ipmz_handle h) {
+  if (!h) return IPMZ_OK;
+  delete h->w;
+  delete h;
+  return IPMZ_OK;
+}
+
+int ipmz_set_iterate(ipmz_handle h, const double* packed) {
+  if (!h || !packed) return fail(IPMZ_ERR_ARG, "null argument");
+  return move_iterates(*h->w, h->mi_host, h->me_host, const_cast<double*>(packed), 0);
+}
+
+int ipmz_get_iterate(ipmz_handle h, double* packed) {
+  if (!h || !packed) return fail(IPMZ_ERR_ARG, "null argument");
+  return move_iterates(*h->w, h->mi_host, h->me_host, packed, 1);
+}
+
+int ipmz_reset_iterate(ipmz_handle h) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  View v = w.v;
+  v.active = nullptr;
+  launch_initial_point(w.st, v, w.count);
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  return IPMZ_OK;
+}
+
+int ipmz_solve(ipmz_handle h, ipmz_result* res) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  // a fresh solve restarts the per-problem counters but keeps the iterate (warm start
+  // semantics of the reference: the Environment persists across solve() calls)
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  std::vector<Scal> zero(w.count);
+  std::memset(zero.data(), 0, sizeof(Scal) * w.count);
+  CUDA_TRY(cudaMemcpy(w.v.sc, zero.data(), sizeof(Scal) * w.count, cudaMemcpyHostToDevice));
+  double ms = 0.0;
+  if ((rc = run_ipm(w, &ms))) return rc;
+  if (res) fill_result(w, 0, res, ms);
+  return IPMZ_OK;
+}
+
+int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* alpha_aff, double* sigma,
+                     double* alpha) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  View v = w.v;
+  v.active = nullptr;
+  const Shape& s = v.s;
+  iteration_matvecs(w, v, 1);
+  launch_residuals_rhs(w.st, v, 1, 0);
+  newton_iteration(w, v, 1, false, -1);
+  CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal), cudaMemcpyDeviceToHost, w.st));
+  double* outs[2] = {step_aff, step_cor};
+  const double* packs[2] = {v.DA, v.D};
+  for (int k = 0; k < 2; ++k) {
+    if (!outs[k]) continue;
+    CUDA_TRY(cudaMemcpyAsync(outs[k], packs[k], sizeof(double) * s.n, cudaMemcpyDeviceToHost, w.st));
+    if (s.m > 0)
+      CUDA_TRY(cudaMemcpyAsync(outs[k] + s.n, packs[k] + (size_t)N_NSLOTS * s.ns, sizeof(double) * s.m,
+                               cudaMemcpyDeviceToHost, w.st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  CUDA_TRY(cudaGetLastError());
+  if (alpha_aff) *alpha_aff = w.sc_host[0].alpha_aff;
+  if (sigma) *sigma = w.sc_host[0].sigma;
+  if (alpha) *alpha = w.sc_host[0].alpha;
+  return IPMZ_OK;
+}
+
+int ipmz_get_trace(ipmz_handle h, int cap, double* f, double* res, double* mu, double* step_aff, double* step_cor,
+                   double* alpha_aff, double* sigma, double* alpha) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  const int nlog = (int)w.tr_f.size();
+  for (int i = 0; i < nlog && i < cap; ++i) {
+    if (f) f[i] = w.tr_f[i];
+    if (res) res[i] = w.tr_res[i];
+    if (mu) mu[i] = w.tr_mu[i];
+  }
+  const int nst = (int)w.tr_alpha.size();
+  for (int i = 0; i < nst && i < cap; ++i) {
+    if (alpha_aff) alpha_aff[i] = w.tr_alpha_aff[i];
+    if (sigma) sigma[i] = w.tr_sigma[i];
+    if (alpha) alpha[i] = w.tr_alpha[i];
+  }
+  if ((step_aff || step_cor)) {
+    if (!w.steps_dev) return fail(IPMZ_ERR_ARG, "steps were not recorded (options.record_steps)");
+    if (ensure_device(w.device)) return IPMZ_ERR_CUDA;
+    const int k = std::min(cap, w.tr_iters);
+    for (int i = 0; i < k; ++i) {
+      if (step_aff)
+        CUDA_TRY(cudaMemcpy(step_aff + (size_t)i * w.Naug, w.steps_dev + (size_t)i * 2 * w.Naug,
+                            sizeof(double) * w.Naug, cudaMemcpyDeviceToHost));
+      if (step_cor)
+        CUDA_TRY(cudaMemcpy(step_cor + (size_t)i * w.Naug, w.steps_dev + ((size_t)i * 2 + 1) * w.Naug,
+                            sizeof(double) * w.Naug, cudaMemcpyDeviceToHost));
+    }
+  }
+  return IPMZ_OK;
+}
+
+int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out) {
+  if (!h || !K_host) return fail(IPMZ_ERR_ARG, "null argument");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  View v = w.v;
+  v.active = nullptr;
+  iteration_matvecs(w, v, 1);
+  launch_residuals_rhs(w.st, v, 1, 0);
+  assemble_and_factor(w, v, 1);
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  const int N = v.N;
+  CUDA_TRY(cudaMemcpy2D(K_host, sizeof(double) * N, v.K, sizeof(double) * v.ldk, sizeof(double) * N, N,
+                        cudaMemcpyDeviceToHost));
+  if (v.normal)  // the condensed term is accumulated on the lower triangle only
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) K_host[(size_t)i * N + j] = K_host[(size_t)j * N + i];
+  if (N_out) *N_out = N;
+  return IPMZ_OK;
+}
+
+// ---- batch ------------------------------------------------------------------------------
+int ipmz_batch_create(int count, const ipmz_problem* p, const ipmz_options* opt, ipmz_batch_handle* out) {
+  if (!out) return fail(IPMZ_ERR_ARG, "null out handle");
+  Workspace* w = nullptr;
+  const int rc = create_workspace(&w, count, p, opt);
+  if (rc) return rc;
+  *out = new ipmz_batch_s{w, p->m_ineq, p->m_eq, 0.0};
+  return IPMZ_OK;
+}
+
+int ipmz_batch_destroy(ipmz_batch_handle h) {
+  if (!h) return IPMZ_OK;
+  delete h->w;
+  delete h;
+  return IPMZ_OK;
+}
+
+int ipmz_batch_upload(ipmz_batch_handle h, const ipmz_problem* data) {
+  if (!h || !data) return fail(IPMZ_ERR_ARG, "null argument");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  if ((rc = upload_data(w, data))) return rc;
+  View v = w.v;
+  v.active = nullptr;
+  launch_initial_point(w.st, v, w.count);
+  return IPMZ_OK;
+}
+
+int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem, double* ms_total) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  double ms = 0.0;
+  const int rc = run_ipm(w, &ms);
+  if (rc) return rc;
+  h->last_ms = ms;
+  if (ms_total) *ms_total = ms;
+  if (per_problem)
+    for (int q = 0; q < w.count; ++q) fill_result(w, q, per_problem + q, ms);
+  return IPMZ_OK;
+}
+
+int ipmz_batch_get_iterates(ipmz_batch_handle h, double* packed) {
+  if (!h || !packed) return fail(IPMZ_ERR_ARG, "null argument");
+  return move_iterates(*h->w, h->mi_host, h->me_host, packed, 1);
+}
+
+int ipmz_batch_get_x(ipmz_batch_handle h, double* x) {
+  if (!h || !x) return fail(IPMZ_ERR_ARG, "null argument");
+  Workspace& w = *h->w;
+  if (ensure_device(w.device)) return IPMZ_ERR_CUDA;
+  CUDA_TRY(cudaMemcpy2DAsync(x, sizeof(double) * w.v.s.n, w.v.V, sizeof(double) * w.v.sp, sizeof(double) * w.v.s.n,
+                             w.count, cudaMemcpyDeviceToHost, w.st));
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  return IPMZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, ipm-zoo_b200/capi.py) against the
+CPU oracle (oracle/ipm_oracle.c, itself pinned bit-for-bit to the unmodified reference) and the
+reference-generated goldens, on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): Newton step 1e-9 relative, same iteration count, final
+objective within 1e-8.  Steps are compared norm-wise: max|d_gpu - d_ref| / max|d_ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import problems as P
+from golden.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STEP_TOL = 1e-9
+F_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def z():
+    import ipm_zoo_b200 as z
+    assert z.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return z
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def quasidef(rng, n, m):
+    M = rng.standard_normal((n, n))
+    H = M @ M.T / n + np.eye(n)
+    A = rng.standard_normal((m, n)) / np.sqrt(n)
+    return np.block([[H, A.T], [A, -np.diag(rng.uniform(0.5, 2.0, m))]])
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32, 33, 64, 100, 127, 128, 129, 200, 257, 300, 515])
+def test_ldlt_matches_oracle_spd(z, n):
+    rng = np.random.default_rng(100 + n)
+    M = rng.standard_normal((n, n))
+    A = M @ M.T / n + np.eye(n)
+    L, D = z.ldlt_decomposition(A)
+    Lo, Do = np.zeros((n, n)), np.zeros(n)
+    ol.port().orc_ldlt(n, ol._ptr(np.ascontiguousarray(A)), ol._ptr(Lo), ol._ptr(Do))
+    assert relerr(D, Do) < 1e-11
+    assert relerr(L, Lo) < 1e-11
+    assert np.all(np.triu(L, 1) == 0.0) and np.all(np.diag(L) == 1.0)
+    b = rng.standard_normal(n)
+    x = b.copy()
+    z.overwriting_solve_ldlt(L, D, x)
+    xo = b.copy()
+    ol.port().orc_solve_ldlt(n, ol._ptr(Lo), ol._ptr(Do), ol._ptr(xo))
+    assert relerr(x, xo) < 1e-10
+    assert np.max(np.abs(A @ x - b)) < 1e-9 * max(1.0, np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("n,m", [(3, 2), (40, 17), (128, 64), (200, 100), (300, 140)])
+def test_ldlt_matches_oracle_quasidefinite(z, n, m):
+    rng = np.random.default_rng(7 * n + m)
+    K = np.ascontiguousarray(quasidef(rng, n, m))
+    N = n + m
+    L, D = z.ldlt_decomposition(K)
+    Lo, Do = np.zeros((N, N)), np.zeros(N)
+    ol.port().orc_ldlt(N, ol._ptr(K), ol._ptr(Lo), ol._ptr(Do))
+    assert np.all(D[:n] > 0) and np.all(D[n:] < 0)
+    assert relerr(D, Do) < 1e-10
+    assert relerr(L, Lo) < 1e-10
+    b = rng.standard_normal(N)
+    x = b.copy()
+    z.overwriting_solve_ldlt(L, D, x)
+    assert np.max(np.abs(K @ x - b)) < 1e-9
+
+
+def test_ldlt_golden_reference_vectors(z):
+    g = np.load(os.path.join(GOLD, "linear_solvers.npz"))
+    for nm in ("spd", "quasidef"):
+        L, D = z.ldlt_decomposition(g[nm + "_K"])
+        assert relerr(L, g[nm + "_L"]) < 1e-11
+        assert relerr(D, g[nm + "_D"]) < 1e-11
+        x = g[nm + "_b"].copy()
+        z.overwriting_solve_ldlt(g[nm + "_L"], g[nm + "_D"], x)
+        assert relerr(x, g[nm + "_x"]) < 1e-10
+
+
+def test_ldlt_zero_pivot_guard(z):
+    """LinearSolvers.cpp:28: exactly-zero pivot -> 1e-8."""
+    L, D = z.ldlt_decomposition(np.array([[0.0, 0.0], [0.0, 2.0]]))
+    assert D[0] == 1e-8 and D[1] == 2.0
+
+
+def test_solve_empty_rhs_is_noop(z):
+    """LinearSolvers.cpp:46-48."""
+    b = np.zeros(0)
+    z.overwriting_solve_ldlt(np.zeros((0, 0)), np.zeros(0), b)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("reduction", ["augmented", "normal"])
+def test_assemble_matches_oracle(z, name, reduction):
+    p = CASES[name]()
+    if p.n > 100:
+        pytest.skip("covered by the solve tests")
+    it0 = np.zeros(p.iterate_len)
+    ps = p.c_struct()
+    ol.port().orc_initial_iterate(ps, ol._ptr(it0))
+    N = p.N
+    K = np.zeros((N, N)); rhs = np.zeros(N)
+    ol.port().orc_assemble_kkt(ps, ol._ptr(it0), ol._ptr(K), ol._ptr(rhs))
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=z.NORMAL if reduction == "normal" else z.AUGMENTED))
+    Kg = s.assemble()
+    if reduction == "augmented":
+        assert Kg.shape == (N, N)
+        assert relerr(Kg, K) < 1e-14
+    else:
+        n = p.n
+        H, A, Wd = K[:n, :n], K[n:, :n], -1.0 / np.diag(K)[n:]
+        ref = H + A.T @ (Wd[:, None] * A) if N > n else H
+        assert relerr(Kg, ref) < 1e-12
+    s.close()
+
+
+def _step_parity(z, p, iterate, reduction, tol=STEP_TOL):
+    tr = ol.port_solve(p, cap_iters=1, stop_after_cap=True, iterate=iterate)
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=reduction))
+    if iterate is not None:
+        s.set_iterate(iterate)
+    sa, sc, aa, sg, al = s.newton_step()
+    s.close()
+    assert relerr(sa, tr.step_aff[0]) < tol, "affine step"
+    assert relerr(sc, tr.step_cor[0]) < tol, "corrector step"
+    assert abs(aa - tr.alpha_aff[0]) < 1e-9 * max(1.0, abs(tr.alpha_aff[0]))
+    assert abs(sg - tr.sigma[0]) < 1e-8
+    assert abs(al - tr.alpha[0]) < 1e-9 * max(1.0, abs(tr.alpha[0]))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_newton_step_at_initial_point(z, name, reduction):
+    _step_parity(z, CASES[name](), None, reduction)
+
+
+@pytest.mark.parametrize("name", ["ineq_box_64x32", "eq_box_40x20", "cfg1_eq_box_200x100", "cfg4_unit_256x128"])
+@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("k", [2, 4])
+def test_newton_step_at_reference_iterate(z, name, reduction, k):
+    """Feed the CUDA path the oracle's iterate after k iterations, compare that iteration's steps."""
+    p = CASES[name]()
+    it = ol.port_solve(p, cap_iters=k, stop_after_cap=True).iterate.copy()
+    _step_parity(z, p, it, reduction)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_full_solve_matches_reference_golden(z, name, reduction):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    p = CASES[name]()
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=reduction, record_steps=True))
+    r = s.solve()
+    k = int(g["iterations"])
+    assert r.iterations == k, "iteration count differs from the reference"
+    assert r.converged == bool(g["converged"])
+    assert abs(r.f - g["f"][k]) <= F_TOL * max(1.0, abs(g["f"][k]))
+    tr = s.trace(k, steps=True)
+    np.testing.assert_allclose(tr["f"][:k + 1], g["f"], rtol=1e-7, atol=1e-8)
+    # first iteration's steps start from identical iterates
+    assert relerr(tr["step_aff"][0], g["step_aff"][0]) < STEP_TOL
+    assert relerr(tr["step_cor"][0], g["step_cor"][0]) < STEP_TOL
+    x = s.iterate()
+    n = p.n
+    assert np.max(np.abs(x[:n] - g["iterate"][:n])) < 1e-6
+    s.close()
+
+
+def test_warm_start_second_solve_is_immediate(z):
+    p = CASES["ineq_box_20x10"]()
+    s = z.Solver(z.Problem.from_data(p))
+    r1 = s.solve()
+    r2 = s.solve()
+    assert r1.converged and r2.converged and r2.iterations == 0
+    s.close()
+
+
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_batch_matches_oracle_per_problem(z, reduction):
+    count, n, m = 12, 48, 20
+    probs = [P.ineq_box(n, m, 2000 + i, kind="shift") for i in range(count)]
+    st = lambda key: np.stack([getattr(q, key) for q in probs])
+    bp = z.Problem(st("Q"), st("c"), st("A"), st("l_A"), st("u_A"), None, None, st("l_x"), st("u_x"))
+    bs = z.BatchSolver(bp, count, z.Options(reduction=reduction))
+    res, ms = bs.solve()
+    xs = bs.x()
+    for i, q in enumerate(probs):
+        tr = ol.port_solve(q)
+        assert res[i].iterations == tr.iterations, i
+        assert res[i].converged == bool(tr.converged)
+        assert abs(res[i].f - tr.f[tr.iterations]) <= F_TOL * max(1.0, abs(tr.f[tr.iterations]))
+        assert np.max(np.abs(xs[i] - tr.iterate[:n])) < 1e-6
+    bs.close()
+
+
+def test_error_conventions(z):
+    """Reference: ASSERT(l < u) (EnvironmentBuilder.cpp:10-17) and solve_indefinite_ == ASSERT(false)."""
+    p = CASES["box_30"]()
+    bad = z.Problem.from_data(p)
+    bad.u_x = bad.l_x.copy()
+    with pytest.raises(z.IpmzError) as e:
+        z.Solver(bad)
+    assert e.value.code == 5
+    q = CASES["eq_box_40x20"]()
+    zp = z.Problem.from_data(q)
+    zp.equalities = False
+    with pytest.raises(z.IpmzError) as e:
+        z.Solver(zp)
+    assert e.value.code == 4
