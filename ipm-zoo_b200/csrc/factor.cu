@@ -20,7 +20,15 @@
 
 namespace ipmz {
 
+__device__ long long g_phase_clk[16];
+
 namespace {
+
+#ifdef IPMZ_PHASE_CLOCKS
+#define PHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PHASE(i) do {} while (0)
+#endif
 
 constexpr int NB = 128;  // panel width
 constexpr int SB = 32;   // sub-block factored by one warp
@@ -28,8 +36,8 @@ constexpr int SP = 132;  // shared-memory pitch: 132 mod 16 == 4 -> DMMA fragmen
                          // k = lane%4) of a half-warp hit 16 distinct 8-byte banks
 constexpr int RB = 64;   // panel rows per CTA in k_trsm_panel
 
-constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB) * sizeof(double);
-constexpr size_t TRSM_SMEM = (size_t)((NB + RB) * SP + 2 * NB) * sizeof(double);
+constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB + 2 * 32 + 16 * 96) * sizeof(double);
+constexpr size_t TRSM_SMEM = (size_t)((NB + RB) * SP + NB + 16 * 96) * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -58,6 +66,18 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// 1/d to <= 1 ulp: MUFU.RCP64H seed + two Newton steps (~50 cycles on the dependent chain of the
+// pivots; the IEEE division sequence is ~70).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 // In shared memory, on the FP64 tensor pipe:  C[rows x cols] -= A[rows x kb] diag(d) B[cols x kb]^T.
 // Each warp takes 16 x 16 output micro-tiles (4 DMMA accumulators).  LOWER: C is the lower
 // triangle of a square block (A and B index the same rows) and only tiles on/below the
@@ -72,6 +92,25 @@ __device__ __forceinline__ void smem_update(double* C, const double* A, const do
     if (LOWER && ni > mi) continue;
     double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
     const int ra = mi * 16 + g, rb = ni * 16 + g;
+    if (kb == SB && mi * 16 + 16 <= rows && ni * 16 + 16 <= cols) {  // warp-uniform: mma.sync needs all lanes
+      // full interior tile: all fragment loads of the 8 k-steps in flight, then 32 DMMAs
+      double af[8][2], bf[8][2];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const double dk = d[s * 4 + q];
+        af[s][0] = A[ra * SP + s * 4 + q];
+        af[s][1] = A[(ra + 8) * SP + s * 4 + q];
+        bf[s][0] = B[rb * SP + s * 4 + q] * dk;
+        bf[s][1] = B[(rb + 8) * SP + s * 4 + q] * dk;
+      }
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        dmma884(acc[0][0], af[s][0], bf[s][0]);
+        dmma884(acc[0][1], af[s][0], bf[s][1]);
+        dmma884(acc[1][0], af[s][1], bf[s][0]);
+        dmma884(acc[1][1], af[s][1], bf[s][1]);
+      }
+    } else
     for (int k = 0; k < kb; k += 4) {
       const int kk = k + q;
       const bool kok = kk < kb;
@@ -99,98 +138,184 @@ __device__ __forceinline__ void smem_update(double* C, const double* A, const do
   }
 }
 
-// One thread owns one row of X (D L^T) = A restricted to a 32-wide column block whose unit-lower
-// factor Lb (pitch SP) and pivots are in shared memory: right-looking substitution, so the 31-c
-// updates of step c are independent FMAs.
-__device__ __forceinline__ void row_solve32(double* row, const double* Lb, const double* dinv, int cb) {
-  double v[SB];
+constexpr int IP = 12;               // pitch of an 8 x 8 inverse block (conflict-free B fragments)
+constexpr int INV_BLK = 8 * IP;      // doubles per inverse block
+constexpr int INV_SUB = 4 * INV_BLK; // per 32-wide sub-block
+
+// Unpivoted LDL^T of one 32 x 32 diagonal sub-block by ONE warp: lane r keeps row r in
+// registers; the finished column c is exchanged through a double-buffered shared-memory line
+// (one store + broadcast loads; shuffles cost ~8 issue cycles per value on this part).  The
+// dependent chain per pivot is FMA -> STS -> LDS -> reciprocal -> MUL.  Then the 8 x 8 blocks
+// Binv_b = D_b^-1 L_bb^-1 (b = 0..3) are formed so that the rows below are solved on the tensor
+// pipe:  X_b = R_b Binv_b^T  with  R_b = A_b - sum_{l<b} X_l D_l L_bl^T.
+__device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* dsm, double* dinv, double* colbuf,
+                                            double* binv, int lane) {
+  double a[SB];
 #pragma unroll
-  for (int c = 0; c < SB; ++c) v[c] = c < cb ? row[c] : 0.0;
+  for (int c = 0; c < SB; ++c) a[c] = (lane < jb && c <= lane) ? S[(j0 + lane) * SP + j0 + c] : 0.0;
 #pragma unroll
   for (int c = 0; c < SB; ++c) {
-    if (c < cb) {
-      const double w = v[c];  // = L_rc * d_c
+    if (c < jb) {
+      double* buf = colbuf + (c & 1) * SB;
+      buf[lane] = a[c];
+      __syncwarp();
+      double col[SB];
 #pragma unroll
       for (int c2 = 0; c2 < SB; ++c2)
-        if (c2 > c && c2 < cb) v[c2] -= w * Lb[c2 * SP + c];
-      v[c] = w * dinv[c];
+        if (c2 >= c) col[c2] = buf[c2];
+      double d = col[c];
+      if (d == 0.0) d = 1e-8;  // LinearSolvers.cpp:28
+      const double rinv = fast_rcp(d);
+      const double l = a[c] * rinv;
+#pragma unroll
+      for (int c2 = 0; c2 < SB; ++c2)
+        if (c2 > c) a[c2] -= l * col[c2];
+      if (lane == c) { dsm[j0 + c] = d; dinv[j0 + c] = rinv; }
+      if (lane > c) a[c] = l;
     }
   }
 #pragma unroll
   for (int c = 0; c < SB; ++c)
-    if (c < cb) row[c] = v[c];
+    if (lane < jb && c < lane) S[(j0 + lane) * SP + j0 + c] = a[c];
+  __syncwarp();
+  // lane (b, j): column j of L_bb^-1 by forward substitution, scaled by D^-1
+  {
+    const int bb = lane >> 3, j = lane & 7;
+    const double* Lb = S + (j0 + 8 * bb) * SP + j0 + 8 * bb;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < i) s += ((8 * bb + i < jb && k >= j) ? Lb[i * SP + k] : 0.0) * x[k];
+      if (i > j) x[i] = -s;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const double dn = (8 * bb + n < jb) ? dinv[j0 + 8 * bb + n] : 0.0;
+      binv[bb * INV_BLK + n * IP + j] = (n >= j) ? dn * x[n] : 0.0;
+    }
+  }
+}
+
+// Rows [0, nrows) of T (shared, pitch SP), columns [c0, c0+32):  X (D L^T) = A on the tensor
+// pipe.  L = the unit-lower 32 x 32 block at Lb (pitch SP), d its pivots, binv its four
+// D^-1 L^-1 blocks.  Each warp owns 16-row tiles and runs the four 8-column stages on them
+// without block-level synchronisation (rows are independent).
+__device__ __forceinline__ void panel_solve32(double* T, int nrows, const double* Lb, const double* d,
+                                              const double* binv, int warp, int lane, int nwarps) {
+  const int g = lane >> 2, q = lane & 3;
+  for (int mt = warp; mt * 16 < nrows; mt += nwarps) {
+    double* T0 = T + (mt * 16 + g) * SP;
+    double* T1 = T0 + 8 * SP;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double acc0[2], acc1[2];
+      acc0[0] = T0[8 * b + 2 * q]; acc0[1] = T0[8 * b + 2 * q + 1];
+      acc1[0] = T1[8 * b + 2 * q]; acc1[1] = T1[8 * b + 2 * q + 1];
+      if (b > 0) {
+        double af0[6], af1[6], bf[6];
+#pragma unroll
+        for (int s = 0; s < 2 * b; ++s) {
+          const int k = 4 * s + q;
+          af0[s] = T0[k];
+          af1[s] = T1[k];
+          bf[s] = -(Lb[(8 * b + g) * SP + k] * d[k]);
+        }
+#pragma unroll
+        for (int s = 0; s < 2 * b; ++s) {
+          dmma884(acc0, af0[s], bf[s]);
+          dmma884(acc1, af1[s], bf[s]);
+        }
+        T0[8 * b + 2 * q] = acc0[0]; T0[8 * b + 2 * q + 1] = acc0[1];
+        T1[8 * b + 2 * q] = acc1[0]; T1[8 * b + 2 * q + 1] = acc1[1];
+        __syncwarp();
+      }
+      double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+      const double r00 = T0[8 * b + q], r01 = T0[8 * b + 4 + q];
+      const double r10 = T1[8 * b + q], r11 = T1[8 * b + 4 + q];
+      const double i0 = binv[b * INV_BLK + g * IP + q], i1 = binv[b * INV_BLK + g * IP + 4 + q];
+      dmma884(x0, r00, i0);
+      dmma884(x1, r10, i0);
+      dmma884(x0, r01, i1);
+      dmma884(x1, r11, i1);
+      __syncwarp();
+      T0[8 * b + 2 * q] = x0[0]; T0[8 * b + 2 * q + 1] = x0[1];
+      T1[8 * b + 2 * q] = x1[0]; T1[8 * b + 2 * q + 1] = x1[1];
+      __syncwarp();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_diag_ldlt(const double* src, double* dst,
                                                    int ld, size_t sK, double* __restrict__ Dg, size_t sD,
+                                                   double* __restrict__ Ginv, size_t sInv,
                                                    int k0, int nb, const int* __restrict__ active) {
   extern __shared__ double sm[];
   double* S = sm;
   double* dsm = sm + NB * SP;
   double* dinv = dsm + NB;
+  double* colbuf = dinv + NB;          // 2 x 32
+  double* binv = colbuf + 2 * SB;      // 4 sub-blocks x 4 blocks x INV_BLK
   const int p = active ? active[blockIdx.y] : blockIdx.y;
   const double* A = src + (size_t)p * sK + (size_t)k0 * ld + k0;
   double* O = dst + (size_t)p * sK + (size_t)k0 * ld + k0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  PHASE(0);
+  // zero-fill so that partial sub-blocks / tiles never read uninitialised shared memory
+  for (int i = tid; i < NB * SP; i += 256) S[i] = 0.0;
+  __syncthreads();
   async_block_load<true>(S, A, ld, nb, nb, tid);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
+  PHASE(1);
 
   for (int j0 = 0; j0 < nb; j0 += SB) {
     const int jb = min(SB, nb - j0);
-    if (warp == 0) {
-      // lane r holds row r of the sub-block; column c is exchanged with shuffles
-      double a[SB];
-#pragma unroll
-      for (int c = 0; c < SB; ++c) a[c] = (lane < jb && c <= lane) ? S[(j0 + lane) * SP + j0 + c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < SB; ++c) {
-        if (c < jb) {
-          const double acol = a[c];
-          double d = __shfl_sync(0xffffffffu, acol, c);
-          if (d == 0.0) d = 1e-8;  // LinearSolvers.cpp:28
-          const double rinv = __drcp_rn(d);
-          const double l = acol * rinv;
-#pragma unroll
-          for (int c2 = c + 1; c2 < SB; ++c2) {
-            const double o = __shfl_sync(0xffffffffu, acol, c2);
-            a[c2] -= l * o;
-          }
-          if (lane == c) { dsm[j0 + c] = d; dinv[j0 + c] = rinv; }
-          if (lane > c) a[c] = l;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < SB; ++c)
-        if (lane < jb && c < lane) S[(j0 + lane) * SP + j0 + c] = a[c];
-    }
+    if (j0 == 0) PHASE(2);
+    if (warp == 0) warp_ldlt32(S, j0, jb, dsm, dinv, colbuf, binv + (j0 / SB) * INV_SUB, lane);
     __syncthreads();
+    if (j0 == 0) PHASE(3);
     const int base = j0 + jb, rem = nb - base;
-    if (tid < rem) row_solve32(S + (base + tid) * SP + j0, S + j0 * SP + j0, dinv + j0, jb);
-    __syncthreads();
-    if (rem > 0)
+    if (rem > 0) {
+      panel_solve32(S + base * SP + j0, rem, S + j0 * SP + j0, dsm + j0, binv + (j0 / SB) * INV_SUB, warp, lane, 8);
+      __syncthreads();
+      if (j0 == 0) PHASE(4);
       smem_update<true>(S + base * SP + base, S + base * SP + j0, S + base * SP + j0, dsm + j0, rem, rem, jb,
                         warp, lane, 8);
-    __syncthreads();
+      __syncthreads();
+      if (j0 == 0) PHASE(5);
+    }
   }
+  PHASE(6);
 
   for (int r = warp; r < nb; r += 8) {
     for (int c = lane; c < r; c += 32) O[(size_t)r * ld + c] = S[r * SP + c];
     if (lane == 0) O[(size_t)r * ld + r] = dsm[r];
   }
   for (int t = tid; t < nb; t += 256) Dg[(size_t)p * sD + k0 + t] = dsm[t];
+  {
+    double* gi = Ginv + (size_t)p * sInv + (size_t)(k0 / 8) * INV_BLK;
+    const int nblk = (nb + SB - 1) / SB * 4;
+    for (int t = tid; t < nblk * INV_BLK; t += 256) gi[t] = binv[t];
+  }
+  PHASE(7);
 }
 
 __global__ void __launch_bounds__(256) k_trsm_panel(const double* src, double* dst,
                                                     int ld, size_t sK, const double* __restrict__ Dg, size_t sD,
+                                                    const double* __restrict__ Ginv, size_t sInv,
                                                     int k0, int nb, int N, const int* __restrict__ active) {
   extern __shared__ double sm[];
   double* S = sm;                  // L_kk (strict lower)
   double* T = sm + NB * SP;        // this CTA's rows of the panel
   double* dsm = T + RB * SP;
-  double* dinv = dsm + NB;
+  double* binv = dsm + NB;
   const int p = active ? active[blockIdx.y] : blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = k0 + nb + blockIdx.x * RB;
@@ -199,25 +324,31 @@ __global__ void __launch_bounds__(256) k_trsm_panel(const double* src, double* d
   const double* Ain = src + (size_t)p * sK + (size_t)r0 * ld + k0;
   double* Aout = dst + (size_t)p * sK + (size_t)r0 * ld + k0;
 
+  if (nb < NB || nr < RB) {
+    for (int i = tid; i < (NB + RB) * SP; i += 256) sm[i] = 0.0;
+    __syncthreads();
+  }
   async_block_load<true>(S, Lkk, ld, nb, nb, tid);
   async_block_load<false>(T, Ain, ld, nr, nb, tid);
   cp_async_commit();
-  for (int t = tid; t < nb; t += 256) {
-    const double d = Dg[(size_t)p * sD + k0 + t];
-    dsm[t] = d;
-    dinv[t] = __drcp_rn(d);
+  for (int t = tid; t < nb; t += 256) dsm[t] = Dg[(size_t)p * sD + k0 + t];
+  {
+    const double* gi = Ginv + (size_t)p * sInv + (size_t)(k0 / 8) * INV_BLK;
+    const int nblk = (nb + SB - 1) / SB * 4;
+    for (int t = tid; t < nblk * INV_BLK; t += 256) binv[t] = gi[t];
   }
   cp_async_wait<0>();
   __syncthreads();
 
   for (int c0 = 0; c0 < nb; c0 += SB) {
     const int cb = min(SB, nb - c0);
-    if (tid < nr) row_solve32(T + tid * SP + c0, S + c0 * SP + c0, dinv + c0, cb);
+    panel_solve32(T + c0, nr, S + c0 * SP + c0, dsm + c0, binv + (c0 / SB) * INV_SUB, warp, lane, 8);
     __syncthreads();
     const int base = c0 + cb, rem = nb - base;
-    if (rem > 0)
+    if (rem > 0) {
       smem_update<false>(T + base, T + c0, S + base * SP + c0, dsm + c0, nr, rem, cb, warp, lane, 8);
-    __syncthreads();
+      __syncthreads();
+    }
   }
 
   for (int r = warp; r < nr; r += 8)
@@ -252,9 +383,8 @@ struct SyrkArgs {
   int rows, kdim;
   double sign;
   const int* active;
-  int tn;        // number of BN-wide tile columns
-  int tj_limit;  // only tile columns < tj_limit are updated (look-ahead split); <= 0: all
-  int tj_first;  // first tile column handled by this launch
+  int tn;    // number of BN-wide tile columns
+  int mode;  // 0: all tiles on/below the diagonal; 1: first block column only; 2: all but the first
 };
 
 __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
@@ -267,12 +397,22 @@ __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
   // linear index over the tiles on/below the diagonal: row block ti holds TILE_RATIO*(ti+1)
   // column tiles (the last row block is clipped to tn)
   const int t = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * (double)t / TILE_RATIO + 1.0) - 1.0) * 0.5);
-  while (TILE_RATIO * ti * (ti + 1) / 2 > t) --ti;
-  while (TILE_RATIO * (ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  const int tj = t - TILE_RATIO * ti * (ti + 1) / 2;
+  int ti, tj;
+  if (a.mode == 1) {  // look-ahead: only the first BM-wide block column
+    ti = t / TILE_RATIO;
+    tj = t - ti * TILE_RATIO;
+  } else if (a.mode == 2) {  // everything but the first block column: row ti >= 1 holds TILE_RATIO*ti tiles
+    ti = (int)((1.0 + sqrt(1.0 + 8.0 * (double)t / TILE_RATIO)) * 0.5);
+    while (TILE_RATIO * ti * (ti - 1) / 2 > t) --ti;
+    while (TILE_RATIO * (ti + 1) * ti / 2 <= t) ++ti;
+    tj = t - TILE_RATIO * ti * (ti - 1) / 2 + TILE_RATIO;
+  } else {
+    ti = (int)((sqrt(8.0 * (double)t / TILE_RATIO + 1.0) - 1.0) * 0.5);
+    while (TILE_RATIO * ti * (ti + 1) / 2 > t) --ti;
+    while (TILE_RATIO * (ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    tj = t - TILE_RATIO * ti * (ti + 1) / 2;
+  }
   if (tj >= a.tn) return;
-  if (tj < a.tj_first || (a.tj_limit > 0 && tj >= a.tj_limit)) return;
   const int row0 = ti * BM, col0 = tj * BN;
 
   const double* P = a.P + (size_t)p * a.sP;
@@ -395,32 +535,92 @@ int factor_init() {
   return (int)e;
 }
 
-void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
-                     size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
-                     int kdim, double sign) {
+static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout,
+                             int ldc, size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd,
+                             int rows, int kdim, double sign, int mode) {
   if (rows <= 0 || kdim <= 0 || nslots <= 0) return;
   const int T = (rows + BM - 1) / BM;
-  SyrkArgs a{Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, active, (rows + BN - 1) / BN, 0, 0};
-  dim3 grid(TILE_RATIO * T * (T + 1) / 2, nslots);
+  int tiles;
+  if (mode == 1) tiles = TILE_RATIO * T;
+  else if (mode == 2) tiles = TILE_RATIO * T * (T - 1) / 2;
+  else tiles = TILE_RATIO * T * (T + 1) / 2;
+  if (tiles <= 0) return;
+  SyrkArgs a{Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, active, (rows + BN - 1) / BN, mode};
+  dim3 grid(tiles, nslots);
   k_syrk_ldl<<<grid, 256, SYRK_SMEM, st>>>(a); count_launch();
 }
 
+void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
+                     size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
+                     int kdim, double sign) {
+  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, 0);
+}
+
 void launch_ldlt(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg) {
+  const LookAhead* la = fp.la;
+  const bool overlap = la && la->side && fp.N > 4 * NB;
   for (int k0 = 0; k0 < fp.N; k0 += NB) {
     const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
     const double* in = (k0 == 0) ? src : dst;
-    k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, k0, nb, fp.active); count_launch();
-    const int rem = fp.N - k0 - nb;
-    if (rem > 0) {
-      k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
-                                                                                 k0, nb, fp.N, fp.active); count_launch();
-      const size_t off = (size_t)(k0 + nb) * fp.ld + (k0 + nb);
-      launch_syrk_ldl(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK,
-                      dst + (size_t)(k0 + nb) * fp.ld + k0, fp.ld, fp.sK, Dg + k0, fp.sD, rem, nb, -1.0);
+    if (!overlap || k0 == 0) {
+      k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb, fp.active);
+      count_launch();
     }
+    const int rem = fp.N - k0 - nb;
+    if (rem <= 0) break;
+    if (!overlap || k0 == 0) {
+      k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
+                                                                                 fp.inv, fp.sInv, k0, nb, fp.N, fp.active);
+      count_launch();
+    }
+    const size_t off = (size_t)(k0 + nb) * fp.ld + (k0 + nb);
+    const double* Pk = dst + (size_t)(k0 + nb) * fp.ld + k0;
+    if (!overlap) {
+      launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
+                       fp.sD, rem, nb, -1.0, 0);
+      continue;
+    }
+    // Look-ahead: update the next block column first, factor it on the high-priority side
+    // stream while the main stream updates the rest of the trailing matrix with panel k.
+    launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
+                     fp.sD, rem, nb, -1.0, 1);
+    cudaEventRecord(la->e_col, st);
+    cudaStreamWaitEvent(la->side, la->e_col, 0);
+    {
+      const int k1 = k0 + nb;
+      const int nb1 = fp.N - k1 < NB ? fp.N - k1 : NB;
+      k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, la->side>>>(dst, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv,
+                                                                    fp.sInv, k1, nb1, fp.active);
+      count_launch();
+      const int rem1 = fp.N - k1 - nb1;
+      if (rem1 > 0) {
+        k_trsm_panel<<<dim3((rem1 + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, la->side>>>(
+            dst, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k1, nb1, fp.N, fp.active);
+        count_launch();
+      }
+    }
+    cudaEventRecord(la->e_panel, la->side);
+    launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
+                     fp.sD, rem, nb, -1.0, 2);
+    cudaStreamWaitEvent(st, la->e_panel, 0);
   }
 }
 
+int lookahead_create(LookAhead* la) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaError_t e = cudaStreamCreateWithPriority(&la->side, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la->e_col, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la->e_panel, cudaEventDisableTiming);
+  return (int)e;
+}
+
+void lookahead_destroy(LookAhead* la) {
+  if (la->e_col) cudaEventDestroy(la->e_col);
+  if (la->e_panel) cudaEventDestroy(la->e_panel);
+  if (la->side) cudaStreamDestroy(la->side);
+  la->side = nullptr; la->e_col = nullptr; la->e_panel = nullptr;
+}
 
 int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
                          double ms[3], double* flops_syrk, int* n_syrk) {
@@ -437,14 +637,14 @@ int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* sr
     const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
     const double* in = (k0 == 0) ? src : dst;
     begin(0);
-    k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, k0, nb, fp.active);
+    k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb, fp.active);
     count_launch();
     end();
     const int rem = fp.N - k0 - nb;
     if (rem > 0) {
       begin(1);
       k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
-                                                                                 k0, nb, fp.N, fp.active);
+                                                                                 fp.inv, fp.sInv, k0, nb, fp.N, fp.active);
       count_launch();
       end();
       const size_t off = (size_t)(k0 + nb) * fp.ld + (k0 + nb);
@@ -482,6 +682,10 @@ __global__ void k_dmma_probe(double* out, int iters) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 }  // namespace
+
+int read_phase_clocks(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(long long) * 16);
+}
 
 int fp64_peak_probe(cudaStream_t st, double* tflops) {
   int dev = 0, sms = 0;

@@ -32,6 +32,14 @@ void launch_update(cudaStream_t st, const View& v, int nslots);
 void launch_assemble(cudaStream_t st, const View& v, int nslots);
 
 // ---- factor.cu ----
+// Side stream + events of the look-ahead schedule of launch_ldlt (one per handle).
+struct LookAhead {
+  cudaStream_t side = nullptr;  // high priority: panel k+1 while the main stream applies panel k
+  cudaEvent_t e_col = nullptr, e_panel = nullptr;
+};
+int lookahead_create(LookAhead* la);
+void lookahead_destroy(LookAhead* la);
+
 struct FactorPlan {
   int N;        // matrix dimension
   int ld;       // leading dimension (multiple of 4)
@@ -39,7 +47,11 @@ struct FactorPlan {
   size_t sD;    // per-problem stride of the pivots
   int nslots;   // problems in this launch
   const int* active;
+  double* inv = nullptr;  // [nslots][(ld/8 + 4) * 96] scratch: D^-1 L^-1 of the 8 x 8 diagonal blocks
+  size_t sInv = 0;
+  const LookAhead* la = nullptr;  // nullptr: single-stream schedule
 };
+inline size_t factor_inv_stride(int ld) { return (size_t)(ld / 8 + 4) * 96; }
 int factor_init();  // opt-in shared memory sizes; returns cudaError_t
 // L, Dg <- LDL^T(src).  src == dst factors in place; otherwise the first panel step reads src
 // and writes dst so no separate copy pass is needed (the reference's ldlt_decomposition is
@@ -51,6 +63,7 @@ int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* sr
                          double ms[3], double* flops_syrk, int* n_syrk);
 // Register-resident DMMA issue-rate probe: the FP64 tensor-pipe ceiling of this device.
 int fp64_peak_probe(cudaStream_t st, double* tflops);
+int read_phase_clocks(long long* out16);  // debug builds (-DIPMZ_PHASE_CLOCKS)
 // C (rows x rows, lower triangle) += sign * P diag(d) P^T with P rows x kdim; the DMMA kernel
 // shared by the trailing update of the factorization (sign -1, P = the panel of L, d = pivots)
 // and the condensed assembly M^T W M (sign +1, P = MT, d = W).

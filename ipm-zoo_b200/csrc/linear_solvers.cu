@@ -26,8 +26,9 @@ using namespace ipmz;
 
 struct ipmz_factor_s {
   int device = 0, n = 0, ld = 0;
-  double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr;
+  double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr, *inv = nullptr;
   TrsvWork tw{};
+  LookAhead la{};
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
@@ -35,6 +36,8 @@ struct ipmz_factor_s {
 static FactorPlan plan(const ipmz_factor_s* h) {
   FactorPlan fp;
   fp.N = h->n; fp.ld = h->ld; fp.sK = (size_t)h->n * h->ld; fp.sD = (size_t)h->ld; fp.nslots = 1; fp.active = nullptr;
+  fp.inv = h->inv; fp.sInv = factor_inv_stride(h->ld);
+  fp.la = &h->la;
   return fp;
 }
 
@@ -53,6 +56,7 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->Dg, sizeof(double) * h->ld);
   if (e == cudaSuccess) e = cudaMalloc(&h->b, sizeof(double) * h->ld);
   if (e == cudaSuccess) e = cudaMalloc(&h->x, sizeof(double) * h->ld);
+  if (e == cudaSuccess) e = cudaMalloc(&h->inv, sizeof(double) * factor_inv_stride(h->ld));
   h->tw.cap_blocks = (n + 63) / 64;
   if (e == cudaSuccess) e = cudaMalloc(&h->tw.flags, sizeof(int) * h->tw.cap_blocks);
   if (e == cudaSuccess) e = cudaMalloc(&h->tw.ticket, sizeof(int));
@@ -63,6 +67,7 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
   if (e == cudaSuccess) e = cudaMemset(h->tw.flags, 0, sizeof(int) * h->tw.cap_blocks);
   if (e == cudaSuccess) e = cudaMemset(h->tw.ticket, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = (cudaError_t)lookahead_create(&h->la);
   if (e == cudaSuccess) e = cudaEventCreate(&h->e0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->e1);
   if (e != cudaSuccess) {
@@ -76,8 +81,9 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
 int ipmz_factor_destroy(ipmz_factor_handle h) {
   if (!h) return IPMZ_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x);
+  cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x); cudaFree(h->inv);
   cudaFree(h->tw.flags); cudaFree(h->tw.ticket);
+  lookahead_destroy(&h->la);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   if (h->st) cudaStreamDestroy(h->st);
@@ -134,7 +140,8 @@ int ipmz_factor_profile(ipmz_factor_handle h, double* ms3, double* flops_syrk, i
   ms3[0] = ms3[1] = ms3[2] = 0.0;
   if (flops_syrk) *flops_syrk = 0.0;
   if (n_syrk) *n_syrk = 0;
-  const FactorPlan fp = plan(h);
+  FactorPlan fp = plan(h);
+  fp.la = nullptr;
   const int e = launch_ldlt_profiled(h->st, fp, h->A, h->L, h->Dg, ms3, flops_syrk, n_syrk);
   if (e != 0) return ipmz_fail(IPMZ_ERR_CUDA, std::string("factor_profile: ") + cudaGetErrorString((cudaError_t)e));
   return IPMZ_OK;
@@ -209,6 +216,8 @@ int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double*
   if (e != cudaSuccess) return ipmz_fail(IPMZ_ERR_CUDA, std::string("solve_ldlt: ") + cudaGetErrorString(e));
   return IPMZ_OK;
 }
+
+int ipmz_debug_phase_clocks(long long* out16) { return read_phase_clocks(out16); }
 
 void* ipmz_host_alloc(size_t bytes) {
   void* p = nullptr;

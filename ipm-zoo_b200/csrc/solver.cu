@@ -79,7 +79,9 @@ struct Workspace {
   double *Q = nullptr, *M = nullptr, *MT = nullptr, *c = nullptr, *lx = nullptr, *ux = nullptr, *lo = nullptr,
          *up = nullptr;
   int* active_dev = nullptr;
+  double* inv = nullptr;
   TrsvWork tw{};
+  LookAhead la{};
   int Naug = 0;
   int refine = 0;  // iterative-refinement steps of the normal reduction
   // host mirrors
@@ -93,6 +95,7 @@ struct Workspace {
 
   ~Workspace() {
     cudaSetDevice(device);
+    lookahead_destroy(&la);
     for (void* p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -227,6 +230,10 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.maxblk = (len + 255) / 256;
 
   CUDA_TRY(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+  if (count == 1) {
+    const int le = lookahead_create(&w->la);
+    if (le != 0) return fail(IPMZ_ERR_CUDA, std::string("lookahead_create: ") + cudaGetErrorString((cudaError_t)le));
+  }
   CUDA_TRY(cudaEventCreate(&w->ev0));
   CUDA_TRY(cudaEventCreate(&w->ev1));
   const size_t C = (size_t)count;
@@ -239,7 +246,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   ALLOC(v.Mx, C * s.ms); ALLOC(v.winv, C * s.ms); ALLOC(v.W, C * s.ms); ALLOC(v.tm, C * s.ms);
   ALLOC(v.rhs, C * (s.ns + s.ms)); ALLOC(v.sol, C * v.ssol);
   ALLOC(v.out, C * (s.ns + s.ms)); ALLOC(v.resid, C * (s.ns + s.ms)); ALLOC(v.Qd, C * s.ns);
-  ALLOC(v.K, C * v.sK); ALLOC(v.Dg, C * v.ldk);
+  ALLOC(v.K, C * v.sK); ALLOC(v.Dg, C * v.ldk); ALLOC(w->inv, C * factor_inv_stride(v.ldk));
   ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
   ALLOC(w->active_dev, C);
   w->tw.cap_blocks = (v.N + 63) / 64;
@@ -263,6 +270,8 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
 static FactorPlan plan_of(const Workspace& w, int nslots, const int* active) {
   FactorPlan fp;
   fp.N = w.v.N; fp.ld = w.v.ldk; fp.sK = w.v.sK; fp.sD = (size_t)w.v.ldk; fp.nslots = nslots; fp.active = active;
+  fp.inv = w.inv; fp.sInv = factor_inv_stride(w.v.ldk);
+  fp.la = (w.count == 1 && w.la.side) ? &w.la : nullptr;
   return fp;
 }
 
