@@ -383,8 +383,9 @@ struct SyrkArgs {
   int rows, kdim;
   double sign;
   const int* active;
-  int tn;    // number of BN-wide tile columns
-  int mode;  // 0: all tiles on/below the diagonal; 1: first block column only; 2: all but the first
+  int tn;     // number of BN-wide tile columns
+  int mode;   // 1: only the first `fcols` BM-wide block columns; otherwise: all but the first `fcols`
+  int fcols;
 };
 
 __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
@@ -398,19 +399,17 @@ __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
   // column tiles (the last row block is clipped to tn)
   const int t = blockIdx.x;
   int ti, tj;
-  if (a.mode == 1) {  // look-ahead: only the first BM-wide block column
-    ti = t / TILE_RATIO;
-    tj = t - ti * TILE_RATIO;
-  } else if (a.mode == 2) {  // everything but the first block column: row ti >= 1 holds TILE_RATIO*ti tiles
-    ti = (int)((1.0 + sqrt(1.0 + 8.0 * (double)t / TILE_RATIO)) * 0.5);
-    while (TILE_RATIO * ti * (ti - 1) / 2 > t) --ti;
-    while (TILE_RATIO * (ti + 1) * ti / 2 <= t) ++ti;
-    tj = t - TILE_RATIO * ti * (ti - 1) / 2 + TILE_RATIO;
-  } else {
-    ti = (int)((sqrt(8.0 * (double)t / TILE_RATIO + 1.0) - 1.0) * 0.5);
-    while (TILE_RATIO * ti * (ti + 1) / 2 > t) --ti;
-    while (TILE_RATIO * (ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    tj = t - TILE_RATIO * ti * (ti + 1) / 2;
+  if (a.mode == 1) {  // only the first a.fcols BM-wide block columns (look-ahead / panel-internal update)
+    const int w = TILE_RATIO * a.fcols;
+    ti = t / w;
+    tj = t - ti * w;
+    if (tj > TILE_RATIO * ti + (TILE_RATIO - 1)) return;  // above the diagonal
+  } else {  // all tiles on/below the diagonal except the first a.fcols block columns
+    int u = (int)((sqrt(8.0 * (double)t / TILE_RATIO + 1.0) - 1.0) * 0.5);
+    while (TILE_RATIO * u * (u + 1) / 2 > t) --u;
+    while (TILE_RATIO * (u + 1) * (u + 2) / 2 <= t) ++u;
+    ti = u + a.fcols;
+    tj = t - TILE_RATIO * u * (u + 1) / 2 + TILE_RATIO * a.fcols;
   }
   if (tj >= a.tn) return;
   const int row0 = ti * BM, col0 = tj * BN;
@@ -537,15 +536,18 @@ int factor_init() {
 
 static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout,
                              int ldc, size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd,
-                             int rows, int kdim, double sign, int mode) {
+                             int rows, int kdim, double sign, int mode, int fcols) {
   if (rows <= 0 || kdim <= 0 || nslots <= 0) return;
   const int T = (rows + BM - 1) / BM;
   int tiles;
-  if (mode == 1) tiles = TILE_RATIO * T;
-  else if (mode == 2) tiles = TILE_RATIO * T * (T - 1) / 2;
-  else tiles = TILE_RATIO * T * (T + 1) / 2;
+  if (mode == 1) {
+    tiles = T * TILE_RATIO * fcols;
+  } else {
+    const int U = T - fcols;
+    tiles = U > 0 ? TILE_RATIO * U * (U + 1) / 2 : 0;
+  }
   if (tiles <= 0) return;
-  SyrkArgs a{Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, active, (rows + BN - 1) / BN, mode};
+  SyrkArgs a{Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, active, (rows + BN - 1) / BN, mode, fcols};
   dim3 grid(tiles, nslots);
   k_syrk_ldl<<<grid, 256, SYRK_SMEM, st>>>(a); count_launch();
 }
@@ -553,57 +555,115 @@ static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, con
 void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
                      size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
                      int kdim, double sign) {
-  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, 0);
+  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, 0, 0);
+}
+
+// Optional per-launch instrumentation (bench roofline): events around every kernel.
+struct LaunchHooks {
+  struct Rec { cudaEvent_t a, b; int kind; };
+  std::vector<Rec>* recs = nullptr;
+  double* flops_syrk = nullptr;
+  int* n_syrk = nullptr;
+  void begin(cudaStream_t st, int kind) const {
+    if (!recs) return;
+    Rec r; r.kind = kind;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    recs->push_back(r);
+  }
+  void end(cudaStream_t st) const {
+    if (recs) cudaEventRecord(recs->back().b, st);
+  }
+};
+
+// diag + panel solve of the NB-wide block column at k0 (reads `in`, writes dst)
+static void launch_panel(cudaStream_t st, const FactorPlan& fp, const double* in, double* dst, double* Dg, int k0,
+                         const LaunchHooks& hk) {
+  const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
+  hk.begin(st, 0);
+  k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb,
+                                                          fp.active);
+  count_launch();
+  hk.end(st);
+  const int rem = fp.N - k0 - nb;
+  if (rem > 0) {
+    hk.begin(st, 1);
+    k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
+                                                                               fp.inv, fp.sInv, k0, nb, fp.N,
+                                                                               fp.active);
+    count_launch();
+    hk.end(st);
+  }
+}
+
+// trailing update of the matrix that starts at row/column c0 with the panel columns [p0, p0+kdim)
+static void launch_trailing(cudaStream_t st, const FactorPlan& fp, const double* in, double* dst, const double* Dg,
+                            int c0, int p0, int kdim, int mode, int fcols, const LaunchHooks& hk) {
+  const int rem = fp.N - c0;
+  if (rem <= 0) return;
+  const size_t off = (size_t)c0 * fp.ld + c0;
+  hk.begin(st, 2);
+  launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, dst + (size_t)c0 * fp.ld + p0,
+                   fp.ld, fp.sK, Dg + p0, fp.sD, rem, kdim, -1.0, mode, fcols);
+  hk.end(st);
+  if (hk.flops_syrk) {
+    // algorithmic flops: lower triangle of the updated region, 2 flops per multiply-add
+    const double r = (double)rem, w = (double)(fcols * BM < rem ? fcols * BM : rem);
+    const double elems = mode == 1 ? (r * w - w * (w - 1) / 2) : (r - w) * (r - w + 1) / 2;
+    *hk.flops_syrk += (double)fp.nslots * 2.0 * elems * (double)kdim;
+    if (hk.n_syrk) *hk.n_syrk += 1;
+  }
+}
+
+// Two NB-wide panels (columns [k0, k0+2NB)) factored back to back: panel A, its update of
+// block column B only, panel B.  After this the trailing matrix can be updated with K = 2NB.
+static void launch_double_panel(cudaStream_t st, const FactorPlan& fp, const double* in, double* dst, double* Dg,
+                                int k0, const LaunchHooks& hk) {
+  launch_panel(st, fp, in, dst, Dg, k0, hk);
+  const int k1 = k0 + NB;
+  if (k1 >= fp.N) return;
+  launch_trailing(st, fp, in, dst, Dg, k1, k0, NB, 1, 1, hk);
+  launch_panel(st, fp, dst, dst, Dg, k1, hk);
+}
+
+static void ldlt_schedule(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
+                          const LaunchHooks& hk, bool allow_overlap) {
+  const LookAhead* la = fp.la;
+  const bool two_level = fp.N > 8 * NB;
+  const bool overlap = allow_overlap && two_level && la && la->side;
+  if (!two_level) {
+    // one panel at a time (small matrices and batches)
+    for (int k0 = 0; k0 < fp.N; k0 += NB) {
+      const double* in = (k0 == 0) ? src : dst;
+      launch_panel(st, fp, in, dst, Dg, k0, hk);
+      launch_trailing(st, fp, in, dst, Dg, k0 + NB, k0, NB, 0, 0, hk);
+    }
+    return;
+  }
+  // Two-level blocking with look-ahead: the trailing matrix is updated with K = 2NB per pass
+  // (half the C traffic and half the per-tile prologue of K = NB); the next double panel is
+  // factored on the high-priority side stream while the main stream updates the rest.
+  const int OB = 2 * NB;
+  launch_double_panel(st, fp, src, dst, Dg, 0, hk);
+  for (int k0 = 0; k0 + OB < fp.N; k0 += OB) {
+    const double* in = (k0 == 0) ? src : dst;
+    const int c0 = k0 + OB;
+    launch_trailing(st, fp, in, dst, Dg, c0, k0, OB, 1, 2, hk);  // next double block column first
+    cudaStream_t ps = st;
+    if (overlap) {
+      cudaEventRecord(la->e_col, st);
+      cudaStreamWaitEvent(la->side, la->e_col, 0);
+      ps = la->side;
+    }
+    launch_double_panel(ps, fp, dst, dst, Dg, c0, hk);
+    if (overlap) cudaEventRecord(la->e_panel, la->side);
+    launch_trailing(st, fp, in, dst, Dg, c0, k0, OB, 0, 2, hk);  // the rest, concurrently
+    if (overlap) cudaStreamWaitEvent(st, la->e_panel, 0);
+  }
 }
 
 void launch_ldlt(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg) {
-  const LookAhead* la = fp.la;
-  const bool overlap = la && la->side && fp.N > 4 * NB;
-  for (int k0 = 0; k0 < fp.N; k0 += NB) {
-    const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
-    const double* in = (k0 == 0) ? src : dst;
-    if (!overlap || k0 == 0) {
-      k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb, fp.active);
-      count_launch();
-    }
-    const int rem = fp.N - k0 - nb;
-    if (rem <= 0) break;
-    if (!overlap || k0 == 0) {
-      k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
-                                                                                 fp.inv, fp.sInv, k0, nb, fp.N, fp.active);
-      count_launch();
-    }
-    const size_t off = (size_t)(k0 + nb) * fp.ld + (k0 + nb);
-    const double* Pk = dst + (size_t)(k0 + nb) * fp.ld + k0;
-    if (!overlap) {
-      launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
-                       fp.sD, rem, nb, -1.0, 0);
-      continue;
-    }
-    // Look-ahead: update the next block column first, factor it on the high-priority side
-    // stream while the main stream updates the rest of the trailing matrix with panel k.
-    launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
-                     fp.sD, rem, nb, -1.0, 1);
-    cudaEventRecord(la->e_col, st);
-    cudaStreamWaitEvent(la->side, la->e_col, 0);
-    {
-      const int k1 = k0 + nb;
-      const int nb1 = fp.N - k1 < NB ? fp.N - k1 : NB;
-      k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, la->side>>>(dst, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv,
-                                                                    fp.sInv, k1, nb1, fp.active);
-      count_launch();
-      const int rem1 = fp.N - k1 - nb1;
-      if (rem1 > 0) {
-        k_trsm_panel<<<dim3((rem1 + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, la->side>>>(
-            dst, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k1, nb1, fp.N, fp.active);
-        count_launch();
-      }
-    }
-    cudaEventRecord(la->e_panel, la->side);
-    launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, Pk, fp.ld, fp.sK, Dg + k0,
-                     fp.sD, rem, nb, -1.0, 2);
-    cudaStreamWaitEvent(st, la->e_panel, 0);
-  }
+  ldlt_schedule(st, fp, src, dst, Dg, LaunchHooks{}, true);
 }
 
 int lookahead_create(LookAhead* la) {
@@ -622,40 +682,39 @@ void lookahead_destroy(LookAhead* la) {
   la->side = nullptr; la->e_col = nullptr; la->e_panel = nullptr;
 }
 
+// Debug: the overlapped schedule with events around every launch; out rows = (kind, start_ms, end_ms)
+// relative to the first launch.  Event records perturb the overlap slightly.
+int launch_ldlt_timeline(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
+                         double* out, int cap, int* nrec) {
+  std::vector<LaunchHooks::Rec> recs;
+  LaunchHooks hk;
+  hk.recs = &recs;
+  cudaEvent_t base;
+  cudaEventCreate(&base);
+  cudaEventRecord(base, st);
+  ldlt_schedule(st, fp, src, dst, Dg, hk, true);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (fp.la && fp.la->side && e == cudaSuccess) e = cudaStreamSynchronize(fp.la->side);
+  int n = 0;
+  for (auto& r : recs) {
+    float t0 = 0.f, t1 = 0.f;
+    if (e == cudaSuccess) { cudaEventElapsedTime(&t0, base, r.a); cudaEventElapsedTime(&t1, base, r.b); }
+    if (n < cap) { out[3 * n] = r.kind; out[3 * n + 1] = t0; out[3 * n + 2] = t1; ++n; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  cudaEventDestroy(base);
+  *nrec = n;
+  return (int)e;
+}
+
 int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
                          double ms[3], double* flops_syrk, int* n_syrk) {
-  struct Rec { cudaEvent_t a, b; int kind; };
-  std::vector<Rec> recs;
-  auto begin = [&](int kind) {
-    Rec r; r.kind = kind;
-    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
-    cudaEventRecord(r.a, st);
-    recs.push_back(r);
-  };
-  auto end = [&]() { cudaEventRecord(recs.back().b, st); };
-  for (int k0 = 0; k0 < fp.N; k0 += NB) {
-    const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
-    const double* in = (k0 == 0) ? src : dst;
-    begin(0);
-    k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb, fp.active);
-    count_launch();
-    end();
-    const int rem = fp.N - k0 - nb;
-    if (rem > 0) {
-      begin(1);
-      k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
-                                                                                 fp.inv, fp.sInv, k0, nb, fp.N, fp.active);
-      count_launch();
-      end();
-      const size_t off = (size_t)(k0 + nb) * fp.ld + (k0 + nb);
-      begin(2);
-      launch_syrk_ldl(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK,
-                      dst + (size_t)(k0 + nb) * fp.ld + k0, fp.ld, fp.sK, Dg + k0, fp.sD, rem, nb, -1.0);
-      end();
-      if (flops_syrk) *flops_syrk += (double)fp.nslots * (double)rem * (double)rem * (double)nb;
-      if (n_syrk) *n_syrk += 1;
-    }
-  }
+  std::vector<LaunchHooks::Rec> recs;
+  LaunchHooks hk;
+  hk.recs = &recs;
+  hk.flops_syrk = flops_syrk;
+  hk.n_syrk = n_syrk;
+  ldlt_schedule(st, fp, src, dst, Dg, hk, false);  // same schedule, serialised on one stream
   cudaError_t e = cudaStreamSynchronize(st);
   for (auto& r : recs) {
     float t = 0.f;

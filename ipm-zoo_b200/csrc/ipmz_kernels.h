@@ -61,6 +61,8 @@ void launch_ldlt(cudaStream_t st, const FactorPlan& fp, const double* src, doubl
 // panel and trailing-update (DMMA) kernels; flops_syrk += algorithmic flops of the updates.
 int launch_ldlt_profiled(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
                          double ms[3], double* flops_syrk, int* n_syrk);
+int launch_ldlt_timeline(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
+                         double* out, int cap, int* nrec);
 // Register-resident DMMA issue-rate probe: the FP64 tensor-pipe ceiling of this device.
 int fp64_peak_probe(cudaStream_t st, double* tflops);
 int read_phase_clocks(long long* out16);  // debug builds (-DIPMZ_PHASE_CLOCKS)

@@ -217,6 +217,13 @@ int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double*
   return IPMZ_OK;
 }
 
+int ipmz_debug_factor_timeline(ipmz_factor_handle h, double* out, int cap, int* nrec) {
+  if (!h) return 1;
+  if (ipmz_ensure_device(h->device)) return 2;
+  const FactorPlan fp = plan(h);
+  return launch_ldlt_timeline(h->st, fp, h->A, h->L, h->Dg, out, cap, nrec);
+}
+
 int ipmz_debug_phase_clocks(long long* out16) { return read_phase_clocks(out16); }
 
 void* ipmz_host_alloc(size_t bytes) {
