@@ -318,7 +318,7 @@ def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
     import problems as P
     total = CFG4["count"] if not args.quick else 64
     n, m = CFG4["n"], CFG4["m"]
-    lo, hi = rank * total // world, (rank + 1) * total // world
+    lo, hi = z.shard_range(total, world, rank)
     cnt = hi - lo
     keys = ("Q", "c", "A", "l_A", "u_A", "l_x", "u_x")
     shapes = dict(Q=(cnt, n, n), c=(cnt, n), A=(cnt, m, n), l_A=(cnt, m), u_A=(cnt, m), l_x=(cnt, n), u_x=(cnt, n))

@@ -15,3 +15,9 @@ done
 wait
 $NVCC -shared -ccbin /usr/bin/g++ -o "$HERE/libipmz_b200.so" "$HERE"/csrc/_obj/*.o -lcudart_static -ldl -lrt -lpthread
 echo "built $HERE/libipmz_b200.so"
+# host-side C++ mirror of the reference interface (over the C ABI) + its demo
+/usr/bin/g++ -std=c++17 -O2 -fPIC -shared -o "$HERE/libipmz_host.so" "$HERE/host/ipmz_numerical_optimization.cpp" \
+  -L"$HERE" -lipmz_b200 -Wl,-rpath,'$ORIGIN'
+/usr/bin/g++ -std=c++17 -O2 -o "$HERE/host/host_demo" "$HERE/host/host_demo.cpp" -L"$HERE" -lipmz_host -lipmz_b200 \
+  -Wl,-rpath,'$ORIGIN/..'
+echo "built $HERE/libipmz_host.so and host/host_demo"

@@ -121,6 +121,12 @@ def device_count():
     return lib().ipmz_device_count()
 
 
+def shard_range(total, world_size, rank):
+    """Contiguous block of problem indices [lo, hi) owned by `rank` when `total` independent QPs
+    are sharded over `world_size` GPUs; no data-path collective."""
+    return rank * total // world_size, (rank + 1) * total // world_size
+
+
 def launch_count():
     return int(lib().ipmz_launch_count())
 
