@@ -39,6 +39,22 @@ __global__ void __launch_bounds__(256) k_assemble(View v) {
   for (int c = v.N + threadIdx.x; c < v.ldk; c += blockDim.x) Krow[c] = 0.0;
 }
 
+__global__ void __launch_bounds__(256) k_scale_cols(const double* __restrict__ in, double* __restrict__ out, int ld,
+                                                    size_t sM, int cols, const double* __restrict__ d, size_t sd,
+                                                    const int* __restrict__ active) {
+  const int p = active ? active[blockIdx.y] : blockIdx.y;
+  const double* src = in + (size_t)p * sM + (size_t)blockIdx.x * ld;
+  double* dst = out + (size_t)p * sM + (size_t)blockIdx.x * ld;
+  const double* dv = d + (size_t)p * sd;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dst[c] = src[c] * dv[c];
+}
+
+void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
+                       size_t sM, int rows, int cols, const double* d, size_t sd) {
+  if (rows <= 0 || cols <= 0 || nslots <= 0) return;
+  k_scale_cols<<<dim3(rows, nslots), 256, 0, st>>>(in, out, ld, sM, cols, d, sd, active); count_launch();
+}
+
 void launch_assemble(cudaStream_t st, const View& v, int nslots) {
   dim3 grid(v.N, nslots);
   k_assemble<<<grid, 256, 0, st>>>(v); count_launch();

@@ -35,6 +35,7 @@ constexpr int SB = 32;   // sub-block factored by one warp
 constexpr int SP = 132;  // shared-memory pitch: 132 mod 16 == 4 -> DMMA fragment loads (row = lane/4,
                          // k = lane%4) of a half-warp hit 16 distinct 8-byte banks
 constexpr int RB = 64;   // panel rows per CTA in k_trsm_panel
+constexpr int WLD = 256; // leading dimension of the scaled-panel buffer W = L D (two NB-wide panels)
 
 constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB + 2 * 32 + 16 * 96) * sizeof(double);
 constexpr size_t TRSM_SMEM = (size_t)((NB + RB) * SP + NB + 16 * 96) * sizeof(double);
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(256) k_diag_ldlt(const double* src, double* ds
 __global__ void __launch_bounds__(256) k_trsm_panel(const double* src, double* dst,
                                                     int ld, size_t sK, const double* __restrict__ Dg, size_t sD,
                                                     const double* __restrict__ Ginv, size_t sInv,
+                                                    double* __restrict__ Wp, size_t sW,
                                                     int k0, int nb, int N, const int* __restrict__ active) {
   extern __shared__ double sm[];
   double* S = sm;                  // L_kk (strict lower)
@@ -351,8 +353,14 @@ __global__ void __launch_bounds__(256) k_trsm_panel(const double* src, double* d
     }
   }
 
+  // L into the factor, W = L D (the pre-scaled B operand of the trailing updates) into the panel buffer
+  double* Wout = Wp + (size_t)p * sW + (size_t)r0 * WLD + (k0 % WLD);
   for (int r = warp; r < nr; r += 8)
-    for (int c = lane; c < nb; c += 32) Aout[(size_t)r * ld + c] = T[r * SP + c];
+    for (int c = lane; c < nb; c += 32) {
+      const double l = T[r * SP + c];
+      Aout[(size_t)r * ld + c] = l;
+      Wout[(size_t)r * WLD + c] = l * dsm[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -367,7 +375,7 @@ constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, WARPS_M = 4, WARPS_N = 2;
 constexpr int MI = BM / (WARPS_M * 8), NI = BN / (WARPS_N * 8);
 constexpr int LDT = BK + 4;
 constexpr int TILE_RATIO = BM / BN;
-constexpr size_t SYRK_SMEM = (size_t)(STAGES * (BM + BN) * LDT + STAGES * BK) * sizeof(double);
+constexpr size_t SYRK_SMEM = (size_t)(STAGES * (BM + BN) * LDT) * sizeof(double);
 static_assert(((BM + BN) * (BK / 2)) % 256 == 0, "stage loads must divide evenly over 256 threads");
 
 struct SyrkArgs {
@@ -375,35 +383,27 @@ struct SyrkArgs {
   double* Cout;
   int ldc;
   size_t sC;
-  const double* P;
-  int ldp;
-  size_t sP;
-  const double* d;
-  size_t sd;
+  const double* PA;  // rows x kdim, A operand (rows of the tile)
+  int lda;
+  size_t sA;
+  const double* PB;  // rows x kdim, B operand = P diag(d), pre-scaled (columns of the tile)
+  int ldb;
+  size_t sB;
   int rows, kdim;
   double sign;
   const int* active;
-  int tn;     // number of BN-wide tile columns
-  int mode;   // 1: only the first `fcols` BM-wide block columns; otherwise: all but the first `fcols`
+  int tn;      // number of BN-wide tile columns
+  int mode;    // 1: only the first `fcols` BM-wide block columns; otherwise: all but the first `fcols`
   int fcols;
+  int ntiles;  // tiles of this launch; CTAs are persistent and stride over them
 };
 
-__global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  double* As = smem;
-  double* Bs = As + STAGES * BM * LDT;
-  double* ds = Bs + STAGES * BN * LDT;
-
-  const int p = a.active ? a.active[blockIdx.y] : blockIdx.y;
-  // linear index over the tiles on/below the diagonal: row block ti holds TILE_RATIO*(ti+1)
-  // column tiles (the last row block is clipped to tn)
-  const int t = blockIdx.x;
-  int ti, tj;
+__device__ __forceinline__ bool syrk_tile(const SyrkArgs& a, int t, int& ti, int& tj) {
   if (a.mode == 1) {  // only the first a.fcols BM-wide block columns (look-ahead / panel-internal update)
     const int w = TILE_RATIO * a.fcols;
     ti = t / w;
     tj = t - ti * w;
-    if (tj > TILE_RATIO * ti + (TILE_RATIO - 1)) return;  // above the diagonal
+    if (tj > TILE_RATIO * ti + (TILE_RATIO - 1)) return false;  // above the diagonal
   } else {  // all tiles on/below the diagonal except the first a.fcols block columns
     int u = (int)((sqrt(8.0 * (double)t / TILE_RATIO + 1.0) - 1.0) * 0.5);
     while (TILE_RATIO * u * (u + 1) / 2 > t) --u;
@@ -411,112 +411,134 @@ __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
     ti = u + a.fcols;
     tj = t - TILE_RATIO * u * (u + 1) / 2 + TILE_RATIO * a.fcols;
   }
-  if (tj >= a.tn) return;
-  const int row0 = ti * BM, col0 = tj * BN;
+  return tj < a.tn;
+}
 
-  const double* P = a.P + (size_t)p * a.sP;
-  const double* dv = a.d + (size_t)p * a.sd;
+__global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = As + STAGES * BM * LDT;
+
+  const int p = a.active ? a.active[blockIdx.y] : blockIdx.y;
+  const double* PA = a.PA + (size_t)p * a.sA;
+  const double* PB = a.PB + (size_t)p * a.sB;
+  const double* Cin = a.Cin + (size_t)p * a.sC;
+  double* Cout = a.Cout + (size_t)p * a.sC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp % WARPS_M, wn = warp / WARPS_M;
   const int g = lane >> 2, q = lane & 3;
-  const int wrow = row0 + wm * (MI * 8), wcol = col0 + wn * (NI * 8);
-
   const int KT = (a.kdim + BK - 1) / BK;
-  auto load_stage = [&](int stage, int kt) {
-    const int kbase = kt * BK;
-    double* Asd = As + stage * BM * LDT;
-    double* Bsd = Bs + stage * BN * LDT;
-#pragma unroll
-    for (int i = 0; i < (BM + BN) * (BK / 2) / 256; ++i) {
-      const int chunk = tid + i * 256;
-      const int r = chunk >> 3, ck = (chunk & 7) * 2;
-      const int k = kbase + ck;
-      const bool isA = r < BM;
-      const int gr = isA ? row0 + r : col0 + (r - BM);
-      const bool ok = (gr < a.rows) && (k < a.kdim);
-      const double* srcp = P + (size_t)(ok ? gr : 0) * a.ldp + (ok ? k : 0);
-      double* dstp = isA ? Asd + r * LDT + ck : Bsd + (r - BM) * LDT + ck;
-      cp_async16(dstp, srcp, ok ? 16 : 0);
-    }
-    if (tid < 8) {
-      const int k = kbase + tid * 2;
-      const bool ok = k < a.kdim;
-      cp_async16(ds + stage * BK + tid * 2, dv + (ok ? k : 0), ok ? 16 : 0);
-    }
-  };
 
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage(s, s);
-    cp_async_commit();
-  }
+  for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+    int ti, tj;
+    if (!syrk_tile(a, t, ti, tj)) continue;
+    const int row0 = ti * BM, col0 = tj * BN;
+    const int wrow = row0 + wm * (MI * 8), wcol = col0 + wn * (NI * 8);
 
-  // Accumulators start from sign*C (all loads independent and in flight while the cp.async
-  // prologue lands), so the epilogue is store-only:  Cout = sign * (sign*Cin + P d P^T).
-  const double* Cin = a.Cin + (size_t)p * a.sC;
-  double* Cout = a.Cout + (size_t)p * a.sC;
-  double acc[MI][NI][2];
+    auto load_stage = [&](int stage, int kt) {
+      const int kbase = kt * BK;
+      double* Asd = As + stage * BM * LDT;
+      double* Bsd = Bs + stage * BN * LDT;
 #pragma unroll
-  for (int mi = 0; mi < MI; ++mi) {
-    const int row = wrow + mi * 8 + g;
-#pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-      const int col = wcol + ni * 8 + 2 * q;
-      double2 cv = make_double2(0.0, 0.0);
-      if (row < a.rows && col <= row) {
-        const size_t off = (size_t)row * a.ldc + col;
-        if (col + 1 <= row) cv = *reinterpret_cast<const double2*>(Cin + off);
-        else cv.x = Cin[off];
+      for (int i = 0; i < (BM + BN) * (BK / 2) / 256; ++i) {
+        const int chunk = tid + i * 256;
+        const int r = chunk >> 3, ck = (chunk & 7) * 2;
+        const int k = kbase + ck;
+        const bool isA = r < BM;
+        const int gr = isA ? row0 + r : col0 + (r - BM);
+        const bool ok = (gr < a.rows) && (k < a.kdim);
+        const double* base = isA ? PA : PB;
+        const int ld = isA ? a.lda : a.ldb;
+        const double* srcp = base + (size_t)(ok ? gr : 0) * ld + (ok ? k : 0);
+        double* dstp = isA ? Asd + r * LDT + ck : Bsd + (r - BM) * LDT + ck;
+        cp_async16(dstp, srcp, ok ? 16 : 0);
       }
-      acc[mi][ni][0] = a.sign * cv.x;
-      acc[mi][ni][1] = a.sign * cv.y;
-    }
-  }
+    };
 
-  for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < KT) load_stage(nk % STAGES, nk);
+    __syncthreads();  // the previous tile's last stage is no longer read by any warp
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < KT) load_stage(s, s);
       cp_async_commit();
     }
-    const int stage = kt % STAGES;
-    const double* Aw = As + stage * BM * LDT + (wm * (MI * 8) + g) * LDT + q;
-    const double* Bw = Bs + stage * BN * LDT + (wn * (NI * 8) + g) * LDT + q;
-    const double* dw = ds + stage * BK + q;
+
+    // Accumulators start from sign*C (all loads independent and in flight while the cp.async
+    // prologue lands), so the epilogue is store-only:  Cout = sign * (sign*Cin + PA PB^T).
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double af[MI], bf[NI];
-      const double dk = dw[kk * 4];
+    for (int mi = 0; mi < MI; ++mi) {
+      const int row = wrow + mi * 8 + g;
 #pragma unroll
-      for (int mi = 0; mi < MI; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
-#pragma unroll
-      for (int ni = 0; ni < NI; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4] * dk;
-#pragma unroll
-      for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+      for (int ni = 0; ni < NI; ++ni) {
+        const int col = wcol + ni * 8 + 2 * q;
+        double2 cv = make_double2(0.0, 0.0);
+        if (row < a.rows && col <= row) {
+          const size_t off = (size_t)row * a.ldc + col;
+          if (col + 1 <= row) cv = *reinterpret_cast<const double2*>(Cin + off);
+          else cv.x = Cin[off];
+        }
+        acc[mi][ni][0] = a.sign * cv.x;
+        acc[mi][ni][1] = a.sign * cv.y;
+      }
     }
-  }
-  cp_async_wait<0>();
+    {
+      // warm L2 with the C tile this CTA visits next, so its accumulator loads do not wait on HBM
+      const int tn2 = t + gridDim.x;
+      int ti2, tj2;
+      if (tn2 < a.ntiles && syrk_tile(a, tn2, ti2, tj2)) {
+        const int r = ti2 * BM + (tid >> 1);
+        const int c = tj2 * BN + (tid & 1) * 32;
+        if (r < a.rows && c <= r) {
+          const double* pf = Cin + (size_t)r * a.ldc + c;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 16));
+        }
+      }
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+        const int nk = kt + STAGES - 1;
+        if (nk < KT) load_stage(nk % STAGES, nk);
+        cp_async_commit();
+      }
+      const int stage = kt % STAGES;
+      const double* Aw = As + stage * BM * LDT + (wm * (MI * 8) + g) * LDT + q;
+      const double* Bw = Bs + stage * BN * LDT + (wn * (NI * 8) + g) * LDT + q;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double af[MI], bf[NI];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+      }
+    }
+    cp_async_wait<0>();
 
 #pragma unroll
-  for (int mi = 0; mi < MI; ++mi) {
-    const int row = wrow + mi * 8 + g;
-    if (row >= a.rows) continue;
+    for (int mi = 0; mi < MI; ++mi) {
+      const int row = wrow + mi * 8 + g;
+      if (row >= a.rows) continue;
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-      const int col = wcol + ni * 8 + 2 * q;
-      if (col > row) continue;  // strictly upper part of a diagonal-crossing tile
-      const size_t off = (size_t)row * a.ldc + col;
-      if (col + 1 <= row) {
-        double2 o;
-        o.x = a.sign * acc[mi][ni][0];
-        o.y = a.sign * acc[mi][ni][1];
-        *reinterpret_cast<double2*>(Cout + off) = o;
-      } else {
-        Cout[off] = a.sign * acc[mi][ni][0];
+      for (int ni = 0; ni < NI; ++ni) {
+        const int col = wcol + ni * 8 + 2 * q;
+        if (col > row) continue;  // strictly upper part of a diagonal-crossing tile
+        const size_t off = (size_t)row * a.ldc + col;
+        if (col + 1 <= row) {
+          double2 o;
+          o.x = a.sign * acc[mi][ni][0];
+          o.y = a.sign * acc[mi][ni][1];
+          *reinterpret_cast<double2*>(Cout + off) = o;
+        } else {
+          Cout[off] = a.sign * acc[mi][ni][0];
+        }
       }
     }
   }
@@ -534,9 +556,11 @@ int factor_init() {
   return (int)e;
 }
 
+static int g_num_sms = 0;
+
 static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout,
-                             int ldc, size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd,
-                             int rows, int kdim, double sign, int mode, int fcols) {
+                             int ldc, size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb,
+                             size_t sB, int rows, int kdim, double sign, int mode, int fcols) {
   if (rows <= 0 || kdim <= 0 || nslots <= 0) return;
   const int T = (rows + BM - 1) / BM;
   int tiles;
@@ -547,15 +571,23 @@ static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, con
     tiles = U > 0 ? TILE_RATIO * U * (U + 1) / 2 : 0;
   }
   if (tiles <= 0) return;
-  SyrkArgs a{Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, active, (rows + BN - 1) / BN, mode, fcols};
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  SyrkArgs a{Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, active, (rows + BN - 1) / BN,
+             mode, fcols, tiles};
+  // One CTA per tile: with the look-ahead schedule the high-priority panel kernels of the side
+  // stream get SM slots as tiles retire (persistent CTAs would hold every slot until the end).
   dim3 grid(tiles, nslots);
   k_syrk_ldl<<<grid, 256, SYRK_SMEM, st>>>(a); count_launch();
 }
 
 void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
-                     size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
+                     size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb, size_t sB, int rows,
                      int kdim, double sign) {
-  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, P, ldp, sP, d, sd, rows, kdim, sign, 0, 0);
+  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, 0, 0);
 }
 
 // Optional per-launch instrumentation (bench roofline): events around every kernel.
@@ -576,6 +608,12 @@ struct LaunchHooks {
   }
 };
 
+// The scaled-panel buffer is double-buffered by outer (2NB-wide) block: with look-ahead the next
+// double panel is written while the trailing update still reads the current one.
+static double* wpanel_of(const FactorPlan& fp, int k0) {
+  return fp.wpanel + (size_t)((k0 / WLD) & 1) * (size_t)fp.N * WLD;
+}
+
 // diag + panel solve of the NB-wide block column at k0 (reads `in`, writes dst)
 static void launch_panel(cudaStream_t st, const FactorPlan& fp, const double* in, double* dst, double* Dg, int k0,
                          const LaunchHooks& hk) {
@@ -589,8 +627,8 @@ static void launch_panel(cudaStream_t st, const FactorPlan& fp, const double* in
   if (rem > 0) {
     hk.begin(st, 1);
     k_trsm_panel<<<dim3((rem + RB - 1) / RB, fp.nslots), 256, TRSM_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD,
-                                                                               fp.inv, fp.sInv, k0, nb, fp.N,
-                                                                               fp.active);
+                                                                               fp.inv, fp.sInv, wpanel_of(fp, k0), fp.sW, k0,
+                                                                               nb, fp.N, fp.active);
     count_launch();
     hk.end(st);
   }
@@ -604,7 +642,8 @@ static void launch_trailing(cudaStream_t st, const FactorPlan& fp, const double*
   const size_t off = (size_t)c0 * fp.ld + c0;
   hk.begin(st, 2);
   launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, dst + (size_t)c0 * fp.ld + p0,
-                   fp.ld, fp.sK, Dg + p0, fp.sD, rem, kdim, -1.0, mode, fcols);
+                   fp.ld, fp.sK, wpanel_of(fp, p0) + (size_t)c0 * WLD + (p0 % WLD), WLD, fp.sW, rem, kdim, -1.0, mode,
+                   fcols);
   hk.end(st);
   if (hk.flops_syrk) {
     // algorithmic flops: lower triangle of the updated region, 2 flops per multiply-add

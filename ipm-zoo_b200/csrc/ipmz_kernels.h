@@ -30,6 +30,9 @@ void launch_update(cudaStream_t st, const View& v, int nslots);
 // diagonal-shifted copy Q + Y^-1 L_y + Z^-1 L_z that the condensed assembly accumulates
 // M^T W M onto (N = n).
 void launch_assemble(cudaStream_t st, const View& v, int nslots);
+// out[r][c] = in[r][c] * d[c] (pre-scaled B operand MT diag(W) of the condensed assembly)
+void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
+                       size_t sM, int rows, int cols, const double* d, size_t sd);
 
 // ---- factor.cu ----
 // Side stream + events of the look-ahead schedule of launch_ldlt (one per handle).
@@ -49,9 +52,12 @@ struct FactorPlan {
   const int* active;
   double* inv = nullptr;  // [nslots][(ld/8 + 4) * 96] scratch: D^-1 L^-1 of the 8 x 8 diagonal blocks
   size_t sInv = 0;
+  double* wpanel = nullptr;  // [nslots][2][N x 256] W = L D of the current panels (pre-scaled B operand)
+  size_t sW = 0;
   const LookAhead* la = nullptr;  // nullptr: single-stream schedule
 };
 inline size_t factor_inv_stride(int ld) { return (size_t)(ld / 8 + 4) * 96; }
+inline size_t factor_wpanel_stride(int N) { return (size_t)2 * N * 256; }  // double-buffered
 int factor_init();  // opt-in shared memory sizes; returns cudaError_t
 // L, Dg <- LDL^T(src).  src == dst factors in place; otherwise the first panel step reads src
 // and writes dst so no separate copy pass is needed (the reference's ldlt_decomposition is
@@ -66,11 +72,12 @@ int launch_ldlt_timeline(cudaStream_t st, const FactorPlan& fp, const double* sr
 // Register-resident DMMA issue-rate probe: the FP64 tensor-pipe ceiling of this device.
 int fp64_peak_probe(cudaStream_t st, double* tflops);
 int read_phase_clocks(long long* out16);  // debug builds (-DIPMZ_PHASE_CLOCKS)
-// C (rows x rows, lower triangle) += sign * P diag(d) P^T with P rows x kdim; the DMMA kernel
-// shared by the trailing update of the factorization (sign -1, P = the panel of L, d = pivots)
-// and the condensed assembly M^T W M (sign +1, P = MT, d = W).
+// C (rows x rows, lower triangle) += sign * PA PB^T with PA, PB rows x kdim and PB = PA diag(d)
+// pre-scaled by its producer; the DMMA kernel shared by the trailing update of the factorization
+// (sign -1, PA = the panel of L, PB = W = L D written by k_trsm_panel) and the condensed assembly
+// M^T W M (sign +1, PA = MT, PB = MT diag(W) written by k_scale_cols).
 void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
-                     size_t sC, const double* P, int ldp, size_t sP, const double* d, size_t sd, int rows,
+                     size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb, size_t sB, int rows,
                      int kdim, double sign);
 
 // ---- trsv.cu ----

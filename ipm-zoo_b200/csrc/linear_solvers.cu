@@ -26,7 +26,7 @@ using namespace ipmz;
 
 struct ipmz_factor_s {
   int device = 0, n = 0, ld = 0;
-  double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr, *inv = nullptr;
+  double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr, *inv = nullptr, *wpanel = nullptr;
   TrsvWork tw{};
   LookAhead la{};
   cudaStream_t st = nullptr;
@@ -37,6 +37,7 @@ static FactorPlan plan(const ipmz_factor_s* h) {
   FactorPlan fp;
   fp.N = h->n; fp.ld = h->ld; fp.sK = (size_t)h->n * h->ld; fp.sD = (size_t)h->ld; fp.nslots = 1; fp.active = nullptr;
   fp.inv = h->inv; fp.sInv = factor_inv_stride(h->ld);
+  fp.wpanel = h->wpanel; fp.sW = factor_wpanel_stride(h->n);
   fp.la = &h->la;
   return fp;
 }
@@ -57,6 +58,7 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->b, sizeof(double) * h->ld);
   if (e == cudaSuccess) e = cudaMalloc(&h->x, sizeof(double) * h->ld);
   if (e == cudaSuccess) e = cudaMalloc(&h->inv, sizeof(double) * factor_inv_stride(h->ld));
+  if (e == cudaSuccess) e = cudaMalloc(&h->wpanel, sizeof(double) * factor_wpanel_stride(h->n));
   h->tw.cap_blocks = (n + 63) / 64;
   if (e == cudaSuccess) e = cudaMalloc(&h->tw.flags, sizeof(int) * h->tw.cap_blocks);
   if (e == cudaSuccess) e = cudaMalloc(&h->tw.ticket, sizeof(int));
@@ -81,7 +83,7 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
 int ipmz_factor_destroy(ipmz_factor_handle h) {
   if (!h) return IPMZ_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x); cudaFree(h->inv);
+  cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x); cudaFree(h->inv); cudaFree(h->wpanel);
   cudaFree(h->tw.flags); cudaFree(h->tw.ticket);
   lookahead_destroy(&h->la);
   if (h->e0) cudaEventDestroy(h->e0);

@@ -80,6 +80,8 @@ struct Workspace {
          *up = nullptr;
   int* active_dev = nullptr;
   double* inv = nullptr;
+  double* wpanel = nullptr;
+  double* MTW = nullptr;  // MT diag(W), B operand of the condensed assembly
   TrsvWork tw{};
   LookAhead la{};
   int Naug = 0;
@@ -247,6 +249,8 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   ALLOC(v.rhs, C * (s.ns + s.ms)); ALLOC(v.sol, C * v.ssol);
   ALLOC(v.out, C * (s.ns + s.ms)); ALLOC(v.resid, C * (s.ns + s.ms)); ALLOC(v.Qd, C * s.ns);
   ALLOC(v.K, C * v.sK); ALLOC(v.Dg, C * v.ldk); ALLOC(w->inv, C * factor_inv_stride(v.ldk));
+  ALLOC(w->wpanel, C * factor_wpanel_stride(v.N));
+  if (v.normal) ALLOC(w->MTW, C * v.sMT);
   ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
   ALLOC(w->active_dev, C);
   w->tw.cap_blocks = (v.N + 63) / 64;
@@ -271,6 +275,7 @@ static FactorPlan plan_of(const Workspace& w, int nslots, const int* active) {
   FactorPlan fp;
   fp.N = w.v.N; fp.ld = w.v.ldk; fp.sK = w.v.sK; fp.sD = (size_t)w.v.ldk; fp.nslots = nslots; fp.active = active;
   fp.inv = w.inv; fp.sInv = factor_inv_stride(w.v.ldk);
+  fp.wpanel = w.wpanel; fp.sW = factor_wpanel_stride(w.v.N);
   fp.la = (w.count == 1 && w.la.side) ? &w.la : nullptr;
   return fp;
 }
@@ -289,8 +294,11 @@ static void iteration_matvecs(Workspace& w, const View& v, int nslots) {
 static void assemble_and_factor(Workspace& w, const View& v, int nslots) {
   const Shape& s = v.s;
   launch_assemble(w.st, v, nslots);
-  if (v.normal && s.m > 0)
-    launch_syrk_ldl(w.st, nslots, v.active, v.K, v.K, v.ldk, v.sK, v.MT, v.ldmt, v.sMT, v.W, s.ms, s.n, s.m, 1.0);
+  if (v.normal && s.m > 0) {
+    launch_scale_cols(w.st, nslots, v.active, v.MT, w.MTW, v.ldmt, v.sMT, s.n, s.m, v.W, s.ms);
+    launch_syrk_ldl(w.st, nslots, v.active, v.K, v.K, v.ldk, v.sK, v.MT, v.ldmt, v.sMT, w.MTW, v.ldmt, v.sMT, s.n,
+                    s.m, 1.0);
+  }
 }
 
 // Normal reduction: condensed solve of the augmented right-hand side rvec = b0|b1,
