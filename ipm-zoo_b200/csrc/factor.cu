@@ -12,6 +12,7 @@
 //                 staged with a 3-deep cp.async pipeline; the only dense contraction of the path.
 // The same k_syrk_ldl forms the condensed matrix Hx + M^T W M of the normal reduction.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -544,24 +545,240 @@ __global__ void __launch_bounds__(256, 2) k_syrk_ldl(SyrkArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised persistent variant of the same update for one large matrix:
+// one CTA per SM (≈205 KB shared memory), 128 x 128 tiles, 16 consumer warps (4 x 4, 32 x 32
+// each) + 1 producer warp.  The producer streams 16-wide k-slices of both operands through a
+// 5-stage ring with cp.async; completion is signalled on per-stage "full" mbarriers
+// (cp.async.mbarrier.arrive) and consumers release slots on "empty" mbarriers, so there is no
+// CTA-wide barrier in the loop and the producer runs ahead across tile boundaries (the next
+// tile's operands arrive while the consumers store C).  CTAs stride over the tile list; the
+// launch uses fewer CTAs than SMs when the look-ahead schedule reserves SMs for the panel
+// kernels of the side stream.
+constexpr int WS_BM = 128, WS_BN = 128, WS_STAGES = 5, WS_CONSUMERS = 16, WS_PRODUCERS = 4;
+constexpr int WS_THREADS = (WS_CONSUMERS + WS_PRODUCERS) * 32;
+constexpr int WS_MI = 4, WS_NI = 4;
+constexpr int WS_STAGE_DOUBLES = (WS_BM + WS_BN) * LDT;
+constexpr size_t WS_SMEM = (size_t)WS_STAGES * WS_STAGE_DOUBLES * sizeof(double) + 2 * WS_STAGES * sizeof(unsigned long long);
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned long long* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+      "@p bra WS_DONE;\n"
+      "bra WS_WAIT;\n"
+      "WS_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ bool ws_tile(const SyrkArgs& a, int t, int& ti, int& tj) {
+  if (a.mode == 1) {
+    ti = t / a.fcols;
+    tj = t - ti * a.fcols;
+    if (tj > ti) return false;
+  } else {
+    int u = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while (u * (u + 1) / 2 > t) --u;
+    while ((u + 1) * (u + 2) / 2 <= t) ++u;
+    ti = u + a.fcols;
+    tj = t - u * (u + 1) / 2 + a.fcols;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) k_syrk_ws(SyrkArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + WS_STAGES * WS_STAGE_DOUBLES);
+  unsigned long long* empty = full + WS_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* PA = a.PA;
+  const double* PB = a.PB;
+  const int KT = (a.kdim + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(full + s, 32 * WS_PRODUCERS);  // one cp.async-completion arrive per producer lane
+      mbar_init(empty + s, WS_CONSUMERS);  // one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= WS_CONSUMERS) {
+    // ---------------- producers (one warp per SM sub-partition) ----------------
+    const int pl = tid - WS_CONSUMERS * 32;  // 0 .. 32*WS_PRODUCERS-1
+    unsigned it = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      int ti, tj;
+      if (!ws_tile(a, t, ti, tj)) continue;
+      const int row0 = ti * WS_BM, col0 = tj * WS_BN;
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const unsigned slot = it % WS_STAGES;
+        mbar_wait(empty + slot, ((it / WS_STAGES) & 1u) ^ 1u);
+        double* Sd = smem + slot * WS_STAGE_DOUBLES;
+        const int kbase = kt * BK;
+#pragma unroll 8
+        for (int i = 0; i < (WS_BM + WS_BN) * (BK / 2) / (32 * WS_PRODUCERS); ++i) {
+          const int chunk = pl + i * 32 * WS_PRODUCERS;
+          const int r = chunk >> 3, ck = (chunk & 7) * 2;
+          const int k = kbase + ck;
+          const bool isA = r < WS_BM;
+          const int gr = isA ? row0 + r : col0 + (r - WS_BM);
+          const bool ok = (gr < a.rows) && (k < a.kdim);
+          const double* srcp = (isA ? PA + (size_t)(ok ? gr : 0) * a.lda : PB + (size_t)(ok ? gr : 0) * a.ldb) + (ok ? k : 0);
+          cp_async16(Sd + r * LDT + ck, srcp, ok ? 16 : 0);
+        }
+        mbar_arrive_cp_async(full + slot);
+      }
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, q = lane & 3;
+  const double* Cin = a.Cin;
+  double* Cout = a.Cout;
+  unsigned it = 0;
+  for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+    int ti, tj;
+    if (!ws_tile(a, t, ti, tj)) continue;
+    const int row0 = ti * WS_BM, col0 = tj * WS_BN;
+    const int wrow = row0 + wm * 32, wcol = col0 + wn * 32;
+    double acc[WS_MI][WS_NI][2];
+#pragma unroll
+    for (int mi = 0; mi < WS_MI; ++mi) {
+      const int row = wrow + mi * 8 + g;
+#pragma unroll
+      for (int ni = 0; ni < WS_NI; ++ni) {
+        const int col = wcol + ni * 8 + 2 * q;
+        double2 cv = make_double2(0.0, 0.0);
+        if (row < a.rows && col <= row) {
+          const size_t off = (size_t)row * a.ldc + col;
+          if (col + 1 <= row) cv = *reinterpret_cast<const double2*>(Cin + off);
+          else cv.x = Cin[off];
+        }
+        acc[mi][ni][0] = a.sign * cv.x;
+        acc[mi][ni][1] = a.sign * cv.y;
+      }
+    }
+    {
+      // warm L2 with the C tile this CTA visits next
+      const int t2 = t + gridDim.x;
+      int ti2, tj2;
+      if (t2 < a.ntiles && ws_tile(a, t2, ti2, tj2)) {
+        const int r = ti2 * WS_BM + (tid >> 2);
+        const int c = tj2 * WS_BN + (tid & 3) * 32;
+        if (r < a.rows && c <= r) {
+          const double* pf = Cin + (size_t)r * a.ldc + c;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 16));
+        }
+      }
+    }
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      const unsigned slot = it % WS_STAGES;
+      mbar_wait(full + slot, (it / WS_STAGES) & 1u);
+      const double* Aw = smem + slot * WS_STAGE_DOUBLES + (wm * 32 + g) * LDT + q;
+      const double* Bw = smem + slot * WS_STAGE_DOUBLES + WS_BM * LDT + (wn * 32 + g) * LDT + q;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        double af[WS_MI], bf[WS_NI];
+#pragma unroll
+        for (int mi = 0; mi < WS_MI; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
+#pragma unroll
+        for (int ni = 0; ni < WS_NI; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4];
+#pragma unroll
+        for (int mi = 0; mi < WS_MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < WS_NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + slot);
+    }
+#pragma unroll
+    for (int mi = 0; mi < WS_MI; ++mi) {
+      const int row = wrow + mi * 8 + g;
+      if (row >= a.rows) continue;
+#pragma unroll
+      for (int ni = 0; ni < WS_NI; ++ni) {
+        const int col = wcol + ni * 8 + 2 * q;
+        if (col > row) continue;
+        const size_t off = (size_t)row * a.ldc + col;
+        if (col + 1 <= row) {
+          double2 o;
+          o.x = a.sign * acc[mi][ni][0];
+          o.y = a.sign * acc[mi][ni][1];
+          *reinterpret_cast<double2*>(Cout + off) = o;
+        } else {
+          Cout[off] = a.sign * acc[mi][ni][0];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
+
+static int g_num_sms = 0;
+static int g_use_ws = 1;      // IPMZ_SYRK_WS=0 selects the 2-CTA/SM kernel everywhere (A/B testing)
+static int g_ws_reserve = 16;  // SMs left to the side stream while the main stream updates
 
 int factor_init() {
   cudaError_t e;
+  if (const char* s = getenv("IPMZ_SYRK_WS")) g_use_ws = atoi(s);
+  if (const char* s = getenv("IPMZ_WS_RESERVE")) g_ws_reserve = atoi(s);
   e = cudaFuncSetAttribute(k_diag_ldlt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_syrk_ldl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
   return (int)e;
 }
 
-static int g_num_sms = 0;
 
 static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout,
                              int ldc, size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb,
                              size_t sB, int rows, int kdim, double sign, int mode, int fcols) {
   if (rows <= 0 || kdim <= 0 || nslots <= 0) return;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (nslots == 1 && rows >= 1024 && g_use_ws) {
+    // warp-specialised persistent kernel, 128 x 128 tiles (fcols counts 128-wide block columns in both)
+    const int T = (rows + WS_BM - 1) / WS_BM;
+    int tiles;
+    if (mode == 1) tiles = T * fcols;
+    else { const int U = T - fcols; tiles = U > 0 ? U * (U + 1) / 2 : 0; }
+    if (tiles <= 0) return;
+    SyrkArgs a{Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, active, 0, mode, fcols, tiles};
+    int ctas = g_num_sms - g_ws_reserve;
+    if (ctas < 1) ctas = 1;
+    if (ctas > tiles) ctas = tiles;
+    k_syrk_ws<<<ctas, WS_THREADS, WS_SMEM, st>>>(a); count_launch();
+    return;
+  }
   const int T = (rows + BM - 1) / BM;
   int tiles;
   if (mode == 1) {
@@ -571,11 +788,6 @@ static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, con
     tiles = U > 0 ? TILE_RATIO * U * (U + 1) / 2 : 0;
   }
   if (tiles <= 0) return;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
   SyrkArgs a{Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, active, (rows + BN - 1) / BN,
              mode, fcols, tiles};
   // One CTA per tile: with the look-ahead schedule the high-priority panel kernels of the side
