@@ -1,0 +1,537 @@
+// ipm-zoo_b200/csrc/dataflow.cu -- persistent dataflow LDL^T: the whole blocked factorization of
+// one large reduced KKT matrix (LinearSolvers::ldlt_decomposition, LinearSolvers.cpp:14-42) in
+// ONE kernel launch, one CTA per SM.
+//
+// The matrix is cut into 128 x 128 tiles and the factorization into DIAG / TRSM / UPD tile tasks
+// (ldlt_schedule.hpp).  CTAs draw tasks from a single ticket counter in the order of a list
+// schedule simulated on the host; every task waits for its inputs on flags in global memory
+// (release/acquire at gpu scope) -- so the critical DIAG -> TRSM -> UPD chain of panel k+1, k+2, ...
+// runs ahead of the bulk trailing updates as far as the data allows (dynamic look-ahead), there
+// are no launch gaps and no wave quantisation between panel steps.
+//
+// CTA = 16 consumer warps + 4 producer warps (warp specialisation):
+//   producers  fetch the next ticket, wait for its dependencies, publish the task to the
+//              consumers through a 2-deep task queue and stream the UPD operands (16-wide
+//              k-slices of L and W = L D) through a 5-stage cp.async ring guarded by full/empty
+//              mbarriers -- they run ahead across task boundaries, so the next task's operands
+//              land while the consumers still store the previous C tile;
+//   consumers  4 x 4 warps of 32 x 32 DMMA (mma.sync.m8n8k4.f64) accumulators per 128 x 128 UPD
+//              tile, initialised from C so the epilogue is store-only; DIAG and TRSM tasks run
+//              bulk-synchronously on the consumer warps with the ring memory re-used as tile
+//              storage (one-warp 32 x 32 LDL^T, tensor-pipe panel solves with 8 x 8 inverses).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "ipmz_kernels.h"
+#include "ldlt_device.cuh"
+#include "ldlt_schedule.hpp"
+
+namespace ipmz {
+
+struct DataflowPlan {
+  int N = 0, ld = 0, nt = 0, ntasks = 0, nsm = 0;
+  int4* d_tasks = nullptr;
+  int* d_flags = nullptr;  // [0] ticket, [1] abort, [2 ..) rdy[nt*nt], cnt[nt*nt]
+  size_t flag_ints = 0;
+  double* W = nullptr;     // N x ld, W = L D (pre-scaled B operand of the updates)
+  long long* d_tlog = nullptr;  // optional: 4 x ntasks (start ns, end ns, smid, wait ns)
+  double sim_makespan_us = 0.0;
+};
+
+namespace {
+
+constexpr int DF_STAGES = 5;
+constexpr int DF_CONSUMERS = 16, DF_PRODUCERS = 4;
+constexpr int DF_CTHREADS = DF_CONSUMERS * 32;
+constexpr int DF_PTHREADS = DF_PRODUCERS * 32;
+constexpr int DF_THREADS = DF_CTHREADS + DF_PTHREADS;
+constexpr int DF_STAGE_DOUBLES = 2 * DF_TILE * LDT;
+constexpr int DF_RING_DOUBLES = DF_STAGES * DF_STAGE_DOUBLES;
+constexpr int DF_BULK_DOUBLES = NB * SP + RB * SP + 2 * NB + 2 * SB + 16 * 96;
+constexpr int DF_DATA_DOUBLES = DF_RING_DOUBLES > DF_BULK_DOUBLES ? DF_RING_DOUBLES : DF_BULK_DOUBLES;
+constexpr size_t DF_SMEM = (size_t)DF_DATA_DOUBLES * sizeof(double) + 256;
+static_assert(DF_TILE == NB && DF_HALF == RB, "tile grid of the schedule = panel geometry of the kernels");
+static_assert(DF_SMEM <= 232448, "shared memory per CTA");
+
+struct DfArgs {
+  const double* src;
+  double* dst;
+  double* W;
+  double* Dg;
+  double* Ginv;
+  const int4* tasks;
+  int* ticket;
+  int* abort;
+  int* rdy;
+  int* cnt;
+  long long* tlog;
+  int N, ld, nt, ntasks;
+};
+
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void csync() { bar_named(2, DF_CTHREADS); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int smid() {
+  int s;
+  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(s));
+  return s;
+}
+
+__device__ __forceinline__ int need_of(const DfArgs& a, int i) { return (a.N - i * DF_TILE) > DF_HALF ? 2 : 1; }
+
+// Executed by the first producer warp: wait until every input of `tk` has been published.
+// One lane per flag; a watchdog turns a scheduler/protocol bug into an error instead of a hang.
+__device__ __forceinline__ void wait_deps(const DfArgs& a, const int4 tk, int lane) {
+  const int type = tk.x & 0xff, i = tk.y, j = tk.z;
+  const int* flag = nullptr;
+  int want = 0;
+  if (type == DF_DIAG) {
+    if (lane == 0) { flag = a.cnt + (size_t)i * a.nt + j; want = j; }
+  } else if (type == DF_TRSM) {
+    if (lane == 0) { flag = a.cnt + (size_t)i * a.nt + j; want = j; }
+    if (lane == 1) { flag = a.rdy + (size_t)j * a.nt + j; want = 1; }
+  } else {
+    const int k0 = tk.w & 0xffff, k1 = tk.w >> 16;
+    if (lane == 0) { flag = a.cnt + (size_t)i * a.nt + j; want = k0; }
+    const int l = lane - 1;
+    if (l >= 0 && (l >> 1) < k1 - k0) {
+      const int k = k0 + (l >> 1), r = (l & 1) ? j : i;
+      flag = a.rdy + (size_t)k * a.nt + r;
+      want = need_of(a, r);
+    }
+  }
+  long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    const bool ok = flag == nullptr || ld_acquire(flag) >= want;
+    if (__all_sync(0xffffffffu, ok)) break;
+    __nanosleep(64);
+    if ((spin & 1023u) == 1023u) {
+      if (t0 == 0) t0 = gtimer();
+      const bool bail = ld_acquire(a.abort) != 0 || gtimer() - t0 > 4000000000LL;
+      if (__any_sync(0xffffffffu, bail)) {
+        if (lane == 0) atomicExch(a.abort, 1);
+        break;
+      }
+    }
+  }
+  __syncwarp();  // lane 0 publishes the task: order it after every lane's acquire
+}
+
+// ---- DIAG(k): LDL^T of the diagonal tile, 16 consumer warps (body of k_diag_ldlt, factor.cu) ----
+__device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k, int tid) {
+  double* S = sm;
+  double* dsm = sm + NB * SP + RB * SP;
+  double* dinv = dsm + NB;
+  double* colbuf = dinv + NB;
+  double* binv = colbuf + 2 * SB;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int k0 = k * NB;
+  const int nb = min(NB, a.N - k0);
+  const double* A = (k == 0 ? a.src : a.dst) + (size_t)k0 * a.ld + k0;
+  double* O = a.dst + (size_t)k0 * a.ld + k0;
+
+  for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
+  csync();
+  async_block_load<true, DF_CTHREADS>(S, A, a.ld, nb, nb, tid);
+  cp_async_commit();
+  cp_async_wait<0>();
+  csync();
+  for (int j0 = 0; j0 < nb; j0 += SB) {
+    const int jb = min(SB, nb - j0);
+    if (warp == 0) warp_ldlt32(S, j0, jb, dsm, dinv, colbuf, binv + (j0 / SB) * INV_SUB, lane);
+    csync();
+    const int base = j0 + jb, rem = nb - base;
+    if (rem > 0) {
+      panel_solve32(S + base * SP + j0, rem, S + j0 * SP + j0, dsm + j0, binv + (j0 / SB) * INV_SUB, warp, lane,
+                    DF_CONSUMERS);
+      csync();
+      smem_update<true>(S + base * SP + base, S + base * SP + j0, S + base * SP + j0, dsm + j0, rem, rem, jb, warp,
+                        lane, DF_CONSUMERS);
+      csync();
+    }
+  }
+  for (int r = warp; r < nb; r += DF_CONSUMERS) {
+    for (int c = lane; c < r; c += 32) O[(size_t)r * a.ld + c] = S[r * SP + c];
+    if (lane == 0) O[(size_t)r * a.ld + r] = dsm[r];
+  }
+  for (int t = tid; t < nb; t += DF_CTHREADS) a.Dg[k0 + t] = dsm[t];
+  {
+    double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
+    const int nblk = (nb + SB - 1) / SB * 4;
+    for (int t = tid; t < nblk * INV_BLK; t += DF_CTHREADS) gi[t] = binv[t];
+  }
+}
+
+// ---- TRSM(i,k,h): 64 rows of the panel below the diagonal tile (body of k_trsm_panel) ----
+__device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i, int k, int h, int tid) {
+  double* S = sm;
+  double* T = sm + NB * SP;
+  double* dsm = T + RB * SP;
+  double* binv = dsm + 2 * NB + 2 * SB;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int k0 = k * NB;
+  const int nb = NB;  // a panel with rows below it is always full width
+  const int r0 = i * DF_TILE + h * RB;
+  const int nr = min(RB, a.N - r0);
+  const double* Lkk = a.dst + (size_t)k0 * a.ld + k0;
+  const double* Ain = (k == 0 ? a.src : a.dst) + (size_t)r0 * a.ld + k0;
+  double* Aout = a.dst + (size_t)r0 * a.ld + k0;
+
+  if (nr < RB) {
+    for (int t = tid; t < RB * SP; t += DF_CTHREADS) T[t] = 0.0;
+    csync();
+  }
+  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, nb, nb, tid);
+  async_block_load<false, DF_CTHREADS>(T, Ain, a.ld, nr, nb, tid);
+  cp_async_commit();
+  for (int t = tid; t < nb; t += DF_CTHREADS) dsm[t] = __ldcg(a.Dg + k0 + t);
+  {
+    const double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
+    for (int t = tid; t < 16 * INV_BLK; t += DF_CTHREADS) binv[t] = __ldcg(gi + t);
+  }
+  cp_async_wait<0>();
+  csync();
+  for (int c0 = 0; c0 < nb; c0 += SB) {
+    panel_solve32(T + c0, nr, S + c0 * SP + c0, dsm + c0, binv + (c0 / SB) * INV_SUB, warp, lane, DF_CONSUMERS);
+    csync();
+    const int base = c0 + SB, rem = nb - base;
+    if (rem > 0) {
+      smem_update<false>(T + base, T + c0, S + base * SP + c0, dsm + c0, nr, rem, SB, warp, lane, DF_CONSUMERS);
+      csync();
+    }
+  }
+  double* Wout = a.W + (size_t)r0 * a.ld + k0;
+  for (int r = warp; r < nr; r += DF_CONSUMERS)
+    for (int c = lane * 2; c < nb; c += 64) {
+      const double l0 = T[r * SP + c], l1 = T[r * SP + c + 1];
+      *reinterpret_cast<double2*>(Aout + (size_t)r * a.ld + c) = make_double2(l0, l1);
+      *reinterpret_cast<double2*>(Wout + (size_t)r * a.ld + c) = make_double2(l0 * dsm[c], l1 * dsm[c + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + DF_DATA_DOUBLES);
+  unsigned long long* empty = full + DF_STAGES;
+  unsigned long long* tq_full = empty + DF_STAGES;
+  unsigned long long* tq_empty = tq_full + 2;
+  int4* tq = reinterpret_cast<int4*>(tq_empty + 2);     // 2 published tasks
+  int4* ptask = tq + 2;                                 // 2 producer-side broadcast slots
+  int* tq_ticket = reinterpret_cast<int*>(ptask + 2);   // ticket numbers of the published tasks
+  int* ptask_ticket = tq_ticket + 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < DF_STAGES; ++s) {
+      mbar_init(full + s, DF_PTHREADS);   // one cp.async-completion arrive per producer thread
+      mbar_init(empty + s, DF_CONSUMERS); // one arrive per consumer warp
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tq_full + s, 1);
+      mbar_init(tq_empty + s, DF_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= DF_CONSUMERS) {
+    // ======================= producers =======================
+    const int pl = tid - DF_CTHREADS;
+    const int pwarp = warp - DF_CONSUMERS;
+    unsigned it = 0, pq = 0;
+    int4 tk;
+    int tnum;
+    auto fetch = [&]() {
+      const int b = pq & 1;
+      if (pwarp == 0) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        int4 x = make_int4(DF_DONE, 0, 0, 0);
+        if (t < a.ntasks) {
+          x = __ldg(a.tasks + t);
+          wait_deps(a, x, lane);
+        }
+        if (lane == 0) { ptask[b] = x; ptask_ticket[b] = t; }
+      }
+      bar_named(1, DF_PTHREADS);
+      tk = ptask[b];
+      tnum = ptask_ticket[b];
+    };
+    fetch();
+    for (;;) {
+      const int slot = pq & 1;
+      if (pl == 0) {
+        mbar_wait(tq_empty + slot, ((pq >> 1) & 1u) ^ 1u);
+        tq[slot] = tk;
+        tq_ticket[slot] = tnum;
+        mbar_arrive(tq_full + slot);
+      }
+      ++pq;
+      const int type = tk.x & 0xff;
+      if (type == DF_DONE) break;
+      if (type == DF_UPD) {
+        const int i = tk.y, j = tk.z, k0 = tk.w & 0xffff, k1 = tk.w >> 16;
+        const int KT = (k1 - k0) * (DF_TILE / BK);
+        const double* PA = a.dst + (size_t)i * DF_TILE * a.ld + (size_t)k0 * DF_TILE;
+        const double* PB = a.W + (size_t)j * DF_TILE * a.ld + (size_t)k0 * DF_TILE;
+        const int rowsA = a.N - i * DF_TILE, rowsB = a.N - j * DF_TILE;
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const unsigned s = it % DF_STAGES;
+          mbar_wait(empty + s, ((it / DF_STAGES) & 1u) ^ 1u);
+          double* Sd = smem + s * DF_STAGE_DOUBLES;
+          const int kbase = kt * BK;
+#pragma unroll 8
+          for (int c = 0; c < 2 * DF_TILE * (BK / 2) / DF_PTHREADS; ++c) {
+            const int chunk = pl + c * DF_PTHREADS;
+            const int r = chunk >> 3, ck = (chunk & 7) * 2;
+            const bool isA = r < DF_TILE;
+            const int rr = isA ? r : r - DF_TILE;
+            const bool ok = rr < (isA ? rowsA : rowsB);
+            const double* srcp = (isA ? PA : PB) + (size_t)(ok ? rr : 0) * a.ld + kbase + ck;
+            cp_async16(Sd + r * LDT + ck, srcp, ok ? 16 : 0);
+          }
+          mbar_arrive_cp_async(full + s);
+        }
+        fetch();
+      } else {
+        __syncthreads();  // consumers own the ring memory for the bulk task
+        fetch();
+        __syncthreads();
+      }
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ======================= consumers =======================
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, q = lane & 3;
+  unsigned it = 0, cq = 0;
+  for (;;) {
+    const int slot = cq & 1;
+    mbar_wait(tq_full + slot, (cq >> 1) & 1u);
+    const int4 tk = tq[slot];
+    const int tnum = tq_ticket[slot];
+    ++cq;
+    const int type = tk.x & 0xff;
+    if (type == DF_DONE) break;
+    long long t_start = 0;
+    if (a.tlog && tid == 0) t_start = gtimer();
+    const int i = tk.y, j = tk.z;
+    if (type == DF_UPD) {
+      const int k0 = tk.w & 0xffff, k1 = tk.w >> 16;
+      const int KT = (k1 - k0) * (DF_TILE / BK);
+      const bool diag = i == j;
+      const int row0 = i * DF_TILE, col0 = j * DF_TILE;
+      const int wrow = row0 + wm * 32, wcol = col0 + wn * 32;
+      const bool live = !diag || wn <= wm;  // warp tiles strictly above the diagonal are skipped
+      const double* Cin = k0 == 0 ? a.src : a.dst;
+      double acc[4][4][2];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int row = wrow + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int col = wcol + ni * 8 + 2 * q;
+          double2 cv = make_double2(0.0, 0.0);
+          if (live && row < a.N && (!diag || col <= row)) {
+            const double* p = Cin + (size_t)row * a.ld + col;
+            if (!diag || col + 1 <= row) cv = __ldcg(reinterpret_cast<const double2*>(p));
+            else cv.x = __ldcg(p);
+          }
+          acc[mi][ni][0] = -cv.x;
+          acc[mi][ni][1] = -cv.y;
+        }
+      }
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const unsigned s = it % DF_STAGES;
+        mbar_wait(full + s, (it / DF_STAGES) & 1u);
+        if (live) {
+          const double* Aw = smem + s * DF_STAGE_DOUBLES + (wm * 32 + g) * LDT + q;
+          const double* Bw = smem + s * DF_STAGE_DOUBLES + DF_TILE * LDT + (wn * 32 + g) * LDT + q;
+#pragma unroll
+          for (int kk = 0; kk < BK / 4; ++kk) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+      }
+      if (live) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const int row = wrow + mi * 8 + g;
+          if (row >= a.N) continue;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int col = wcol + ni * 8 + 2 * q;
+            if (diag && col > row) continue;
+            double* p = a.dst + (size_t)row * a.ld + col;
+            if (!diag || col + 1 <= row) *reinterpret_cast<double2*>(p) = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+            else *p = -acc[mi][ni][0];
+          }
+        }
+      }
+      csync();
+      if (tid == 0) {
+        __threadfence();
+        st_release(a.cnt + (size_t)i * a.nt + j, k1);
+      }
+    } else {
+      __syncthreads();  // producers have published and stopped touching the ring
+      if (type == DF_DIAG) df_diag_task(a, smem, j, tid);
+      else df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid);
+      csync();
+      if (tid == 0) {
+        __threadfence();
+        if (type == DF_DIAG) st_release(a.rdy + (size_t)j * a.nt + j, 1);
+        else red_release_add(a.rdy + (size_t)j * a.nt + i, 1);
+      }
+      __syncthreads();
+    }
+    if (a.tlog && tid == 0) {
+      long long* rec = a.tlog + (size_t)tnum * 4;
+      rec[0] = t_start;
+      rec[1] = gtimer();
+      rec[2] = smid();
+      rec[3] = tk.x | ((long long)tk.w << 32);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tq_empty + slot);
+  }
+}
+
+}  // namespace
+
+int dataflow_init() {
+  return (int)cudaFuncSetAttribute(k_ldlt_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+static double env_double(const char* name, double dflt) {
+  const char* s = getenv(name);
+  return s ? atof(s) : dflt;
+}
+
+int dataflow_min_n() { return env_int("IPMZ_DATAFLOW_MIN_N", 2048); }
+
+int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
+  *out = nullptr;
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  DfModel m;
+  m.workers = nsm;
+  m.kb = env_int("IPMZ_DF_KB", m.kb);
+  m.la = env_int("IPMZ_DF_LA", m.la);
+  m.kmax = env_int("IPMZ_DF_KMAX", m.kmax);
+  if (m.kmax > 15) m.kmax = 15;  // one lane per flag in wait_deps
+  m.diag_us = env_double("IPMZ_DF_DIAG_US", m.diag_us);
+  m.trsm_us = env_double("IPMZ_DF_TRSM_US", m.trsm_us);
+  m.upd_base_us = env_double("IPMZ_DF_UPD_BASE_US", m.upd_base_us);
+  m.upd_panel_us = env_double("IPMZ_DF_UPD_PANEL_US", m.upd_panel_us);
+  DfSchedule s = df_build_schedule(N, m);
+  if (!df_validate_schedule(N, s)) return (int)cudaErrorInvalidValue;
+  DataflowPlan* p = new DataflowPlan;
+  p->N = N; p->ld = ld; p->nt = s.nt; p->ntasks = (int)s.tasks.size(); p->nsm = nsm;
+  p->sim_makespan_us = s.makespan_us;
+  p->flag_ints = 2 + 2 * (size_t)s.nt * s.nt;
+  cudaError_t e = cudaMalloc(&p->d_tasks, sizeof(int4) * s.tasks.size());
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_flags, sizeof(int) * p->flag_ints);
+  if (e == cudaSuccess) e = cudaMalloc(&p->W, sizeof(double) * (size_t)N * ld);
+  if (e == cudaSuccess) e = cudaMemset(p->W, 0, sizeof(double) * (size_t)N * ld);
+  if (e == cudaSuccess) {
+    static_assert(sizeof(DfTask) == sizeof(int4), "DfTask is uploaded as int4");
+    e = cudaMemcpy(p->d_tasks, s.tasks.data(), sizeof(int4) * s.tasks.size(), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W);
+    delete p;
+    return (int)e;
+  }
+  *out = p;
+  return 0;
+}
+
+void dataflow_plan_destroy(DataflowPlan* p) {
+  if (!p) return;
+  cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W); cudaFree(p->d_tlog);
+  delete p;
+}
+
+int dataflow_plan_ntasks(const DataflowPlan* p) { return p ? p->ntasks : 0; }
+double dataflow_plan_sim_us(const DataflowPlan* p) { return p ? p->sim_makespan_us : 0.0; }
+
+static void df_launch(cudaStream_t st, const DataflowPlan& p, const double* src, double* dst, double* Dg, double* Ginv,
+                      long long* tlog) {
+  cudaMemsetAsync(p.d_flags, 0, sizeof(int) * p.flag_ints, st);
+  DfArgs a;
+  a.src = src; a.dst = dst; a.W = p.W; a.Dg = Dg; a.Ginv = Ginv; a.tasks = p.d_tasks;
+  a.ticket = p.d_flags; a.abort = p.d_flags + 1; a.rdy = p.d_flags + 2; a.cnt = a.rdy + (size_t)p.nt * p.nt;
+  a.tlog = tlog;
+  a.N = p.N; a.ld = p.ld; a.nt = p.nt; a.ntasks = p.ntasks;
+  const int ctas = p.nsm < p.ntasks ? p.nsm : p.ntasks;
+  k_ldlt_dataflow<<<ctas, DF_THREADS, DF_SMEM, st>>>(a);
+  count_launch();
+}
+
+void launch_ldlt_dataflow(cudaStream_t st, const DataflowPlan& p, const double* src, double* dst, double* Dg,
+                          double* Ginv) {
+  df_launch(st, p, src, dst, Dg, Ginv, nullptr);
+}
+
+// 0 = ok, 1 = a dependency wait hit the watchdog (results invalid)
+int dataflow_abort_flag(cudaStream_t st, const DataflowPlan& p, int* flag) {
+  cudaError_t e = cudaMemcpyAsync(flag, p.d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return (int)e;
+}
+
+// Debug / tuning: one factorization with a per-task log (start ns, end ns, SM id, task words).
+int launch_ldlt_dataflow_logged(cudaStream_t st, DataflowPlan& p, const double* src, double* dst, double* Dg,
+                                double* Ginv, long long* host_log, int cap_tasks, int* ntasks) {
+  cudaError_t e = cudaSuccess;
+  if (!p.d_tlog) e = cudaMalloc(&p.d_tlog, sizeof(long long) * 4 * (size_t)p.ntasks);
+  if (e != cudaSuccess) return (int)e;
+  cudaMemsetAsync(p.d_tlog, 0, sizeof(long long) * 4 * (size_t)p.ntasks, st);
+  df_launch(st, p, src, dst, Dg, Ginv, p.d_tlog);
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return (int)e;
+  const int n = p.ntasks < cap_tasks ? p.ntasks : cap_tasks;
+  e = cudaMemcpy(host_log, p.d_tlog, sizeof(long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost);
+  *ntasks = n;
+  return (int)e;
+}
+
+}  // namespace ipmz

@@ -43,6 +43,21 @@ struct LookAhead {
 int lookahead_create(LookAhead* la);
 void lookahead_destroy(LookAhead* la);
 
+// ---- dataflow.cu: persistent single-launch LDL^T of one large matrix ----
+struct DataflowPlan;  // task list (host-simulated list schedule), dependency flags, W = L D buffer
+int dataflow_init();
+int dataflow_min_n();  // matrices at least this large use the dataflow kernel (IPMZ_DATAFLOW_MIN_N; 0 = never)
+int dataflow_plan_create(DataflowPlan** out, int N, int ld);
+void dataflow_plan_destroy(DataflowPlan* p);
+int dataflow_plan_ntasks(const DataflowPlan* p);
+double dataflow_plan_sim_us(const DataflowPlan* p);
+void launch_ldlt_dataflow(cudaStream_t st, const DataflowPlan& p, const double* src, double* dst, double* Dg,
+                          double* Ginv);
+int dataflow_abort_flag(cudaStream_t st, const DataflowPlan& p, int* flag);
+// one factorization with a per-task log: 4 x int64 per ticket (start ns, end ns, SM id, task words)
+int launch_ldlt_dataflow_logged(cudaStream_t st, DataflowPlan& p, const double* src, double* dst, double* Dg,
+                                double* Ginv, long long* host_log, int cap_tasks, int* ntasks);
+
 struct FactorPlan {
   int N;        // matrix dimension
   int ld;       // leading dimension (multiple of 4)
@@ -55,6 +70,7 @@ struct FactorPlan {
   double* wpanel = nullptr;  // [nslots][2][N x 256] W = L D of the current panels (pre-scaled B operand)
   size_t sW = 0;
   const LookAhead* la = nullptr;  // nullptr: single-stream schedule
+  DataflowPlan* df = nullptr;     // set (single large matrix): launch_ldlt runs the persistent dataflow kernel
 };
 inline size_t factor_inv_stride(int ld) { return (size_t)(ld / 8 + 4) * 96; }
 inline size_t factor_wpanel_stride(int N) { return (size_t)2 * N * 256; }  // double-buffered

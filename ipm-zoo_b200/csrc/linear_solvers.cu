@@ -29,6 +29,7 @@ struct ipmz_factor_s {
   double *A = nullptr, *L = nullptr, *Dg = nullptr, *b = nullptr, *x = nullptr, *inv = nullptr, *wpanel = nullptr;
   TrsvWork tw{};
   LookAhead la{};
+  DataflowPlan* df = nullptr;
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
@@ -39,6 +40,7 @@ static FactorPlan plan(const ipmz_factor_s* h) {
   fp.inv = h->inv; fp.sInv = factor_inv_stride(h->ld);
   fp.wpanel = h->wpanel; fp.sW = factor_wpanel_stride(h->n);
   fp.la = &h->la;
+  fp.df = h->df;
   return fp;
 }
 
@@ -70,6 +72,8 @@ int ipmz_factor_create(int n, int device, ipmz_factor_handle* out) {
   if (e == cudaSuccess) e = cudaMemset(h->tw.ticket, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = (cudaError_t)lookahead_create(&h->la);
+  if (e == cudaSuccess && dataflow_min_n() > 0 && n >= dataflow_min_n())
+    e = (cudaError_t)dataflow_plan_create(&h->df, n, h->ld);
   if (e == cudaSuccess) e = cudaEventCreate(&h->e0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->e1);
   if (e != cudaSuccess) {
@@ -86,6 +90,7 @@ int ipmz_factor_destroy(ipmz_factor_handle h) {
   cudaFree(h->A); cudaFree(h->L); cudaFree(h->Dg); cudaFree(h->b); cudaFree(h->x); cudaFree(h->inv); cudaFree(h->wpanel);
   cudaFree(h->tw.flags); cudaFree(h->tw.ticket);
   lookahead_destroy(&h->la);
+  dataflow_plan_destroy(h->df);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   if (h->st) cudaStreamDestroy(h->st);
@@ -227,6 +232,21 @@ int ipmz_debug_factor_timeline(ipmz_factor_handle h, double* out, int cap, int* 
 }
 
 int ipmz_debug_phase_clocks(long long* out16) { return read_phase_clocks(out16); }
+
+// Dataflow factorization with its per-task log (tools/df_tasklog.py): 4 x int64 per ticket
+// (start ns, end ns, SM id, task words); *sim_us = makespan of the host-simulated schedule.
+int ipmz_debug_factor_tasklog(ipmz_factor_handle h, long long* out, int cap_tasks, int* ntasks, double* sim_us) {
+  if (!h || !h->df) return 1;
+  if (ipmz_ensure_device(h->device)) return 2;
+  if (sim_us) *sim_us = dataflow_plan_sim_us(h->df);
+  const FactorPlan fp = plan(h);
+  int rc = launch_ldlt_dataflow_logged(h->st, *h->df, h->A, h->L, h->Dg, fp.inv, out, cap_tasks, ntasks);
+  if (rc) return 100 + rc;
+  int ab = 0;
+  rc = dataflow_abort_flag(h->st, *h->df, &ab);
+  return rc ? 100 + rc : (ab ? 3 : 0);
+}
+int ipmz_debug_factor_ntasks(ipmz_factor_handle h) { return (h && h->df) ? dataflow_plan_ntasks(h->df) : 0; }
 
 void* ipmz_host_alloc(size_t bytes) {
   void* p = nullptr;

@@ -84,6 +84,7 @@ struct Workspace {
   double* MTW = nullptr;  // MT diag(W), B operand of the condensed assembly
   TrsvWork tw{};
   LookAhead la{};
+  DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
   int Naug = 0;
   int refine = 0;  // iterative-refinement steps of the normal reduction
   // host mirrors
@@ -98,6 +99,7 @@ struct Workspace {
   ~Workspace() {
     cudaSetDevice(device);
     lookahead_destroy(&la);
+    dataflow_plan_destroy(df);
     for (void* p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -235,6 +237,10 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (count == 1) {
     const int le = lookahead_create(&w->la);
     if (le != 0) return fail(IPMZ_ERR_CUDA, std::string("lookahead_create: ") + cudaGetErrorString((cudaError_t)le));
+    if (dataflow_min_n() > 0 && v.N >= dataflow_min_n()) {
+      const int de = dataflow_plan_create(&w->df, v.N, v.ldk);
+      if (de != 0) return fail(IPMZ_ERR_CUDA, std::string("dataflow_plan_create: ") + cudaGetErrorString((cudaError_t)de));
+    }
   }
   CUDA_TRY(cudaEventCreate(&w->ev0));
   CUDA_TRY(cudaEventCreate(&w->ev1));
@@ -277,6 +283,7 @@ static FactorPlan plan_of(const Workspace& w, int nslots, const int* active) {
   fp.inv = w.inv; fp.sInv = factor_inv_stride(w.v.ldk);
   fp.wpanel = w.wpanel; fp.sW = factor_wpanel_stride(w.v.N);
   fp.la = (w.count == 1 && w.la.side) ? &w.la : nullptr;
+  fp.df = (w.count == 1 && nslots == 1 && !active) ? w.df : nullptr;
   return fp;
 }
 
