@@ -507,6 +507,8 @@ int factor_init() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
   if (e != cudaSuccess) return (int)e;
+  const int te = trsv_init();
+  if (te != 0) return te;
   return dataflow_init();
 }
 

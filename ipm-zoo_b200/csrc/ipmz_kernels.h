@@ -44,7 +44,18 @@ int lookahead_create(LookAhead* la);
 void lookahead_destroy(LookAhead* la);
 
 // ---- dataflow.cu: persistent single-launch LDL^T of one large matrix ----
-struct DataflowPlan;  // task list (host-simulated list schedule), dependency flags, W = L D buffer
+struct DataflowPlan {  // task list (host-simulated list schedule), dependency flags, W = L D buffer
+  int N = 0, ld = 0, nt = 0, ntasks = 0, nsm = 0;
+  int4* d_tasks = nullptr;
+  int* d_flags = nullptr;  // [0] ticket, [1] abort, [2 ..) rdy[nt*nt], cnt[nt*nt]
+  size_t flag_ints = 0;
+  double* W = nullptr;     // N x ld, W = L D (pre-scaled B operand of the updates)
+  double* Zinv = nullptr;  // nt x 128 x 128, Z_k = L_kk^-1 (unit lower; identity-padded ragged tile)
+  double* xl = nullptr;    // 2 x nt*128 self-validating exchange buffers of the solves (forward, backward)
+  int* solve_ticket = nullptr;
+  long long* d_tlog = nullptr;  // optional: 4 x ntasks (start ns, end ns, SM id, task words)
+  double sim_makespan_us = 0.0;
+};
 int dataflow_init();
 int dataflow_min_n();  // matrices at least this large use the dataflow kernel (IPMZ_DATAFLOW_MIN_N; 0 = never)
 int dataflow_plan_create(DataflowPlan** out, int N, int ld);
@@ -97,6 +108,8 @@ void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const doubl
                      int kdim, double sign);
 
 // ---- trsv.cu ----
+int trsv_init();  // opt-in shared memory size of the streaming solves
+void trsv_set_debug_log(long long* dev);  // debug: [2][nblk][8] timestamps of the next streaming solves
 struct TrsvWork {
   int* flags;      // [nslots][nblk]
   int* ticket;     // [1]

@@ -246,6 +246,24 @@ int ipmz_debug_factor_tasklog(ipmz_factor_handle h, long long* out, int cap_task
   rc = dataflow_abort_flag(h->st, *h->df, &ab);
   return rc ? 100 + rc : (ab ? 3 : 0);
 }
+// One solve with the per-block-row timestamps of the streaming sweeps: out[2][nblk][16].
+int ipmz_debug_trsv_log(ipmz_factor_handle h, long long* out, int nblk) {
+  if (!h || !h->df) return 1;
+  if (ipmz_ensure_device(h->device)) return 2;
+  long long* dev = nullptr;
+  const size_t bytes = sizeof(long long) * 2 * (size_t)nblk * 16;
+  if (cudaMalloc(&dev, bytes) != cudaSuccess) return 3;
+  cudaMemset(dev, 0, bytes);
+  const FactorPlan fp = plan(h);
+  cudaMemcpyAsync(h->x, h->b, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, h->st);
+  trsv_set_debug_log(dev);
+  launch_ldlt_solve(h->st, fp, h->L, h->Dg, h->x, (size_t)h->ld, h->tw);
+  trsv_set_debug_log(nullptr);
+  cudaError_t e = cudaStreamSynchronize(h->st);
+  if (e == cudaSuccess) e = cudaMemcpy(out, dev, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  return e == cudaSuccess ? 0 : 100 + (int)e;
+}
 int ipmz_debug_factor_ntasks(ipmz_factor_handle h) { return (h && h->df) ? dataflow_plan_ntasks(h->df) : 0; }
 
 void* ipmz_host_alloc(size_t bytes) {

@@ -6,6 +6,8 @@
 // they multiply are published by the CTAs of earlier block rows (flag per block, release /
 // acquire through __threadfence).  CTAs take their block row from an atomic ticket, so a CTA
 // only ever waits on CTAs that started before it -- no dependence on dispatch order.
+#include <stdlib.h>
+
 #include "ipmz_device.cuh"
 #include "ipmz_kernels.h"
 
@@ -172,11 +174,392 @@ __global__ void __launch_bounds__(256) k_trsv_backward(TrsvArgs a) {
   release_ticket(a, tk);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Streaming solves for one large factor (single matrix, N >= the dataflow threshold):
+//   forward   y_r = L_rr^-1   (b_r       - sum_{j<r} L_rj   y_j)
+//   backward  x_r = L_rr^-T   (y_r / D_r - sum_{j>r} L_jr^T x_j)
+// One CTA per 128-row block row (ticket order = dependency order).  Its off-diagonal tiles
+// stream through a 9-stage cp.async ring of 16 x 128 slices whose addresses do not depend on
+// other CTAs, so HBM latency is hidden and the whole last tile is resident when x_{r-1} arrives.
+// The diagonal tile is prepared while the CTA waits: H = blockdiag(L_bb^-1) L_rr with the 8 x 8
+// inverse blocks of the factorization (the same blocks its panel solves use; no larger explicit
+// inverse -- unpivoted LDL^T of a KKT matrix has |L_ij| >> 1 and a 128 x 128 inverse loses all
+// accuracy), which leaves ONE 8 x 8 product per block step on the dependent chain.  The backward
+// sweep runs the same code on the reversed transpose of the tile (again unit lower triangular).
+// Blocks are exchanged through a self-validating buffer (every entry starts as an all-ones
+// NaN pattern and is polled until it changes: one L2 round trip per hop, no fence, no flag).
+constexpr int SV_TB = 128, SV_SR = 16, SV_SPT = SV_TB / SV_SR, SV_STAGES = SV_SPT + 1, SV_THREADS = 256;
+constexpr int SV_STAGE_DOUBLES = SV_SR * SV_TB;
+constexpr int SV_NBLK8 = SV_TB / 8;
+constexpr int SV_H_DOUBLES = 64 * (SV_NBLK8 * (SV_NBLK8 + 1) / 2);  // block-row packed lower triangle
+constexpr int SV_SMEM_DOUBLES = SV_STAGES * SV_STAGE_DOUBLES + SV_H_DOUBLES + 2 * SV_TB + SV_TB + 16 + 8 * SV_TB;
+constexpr size_t SV_SMEM = (size_t)SV_SMEM_DOUBLES * sizeof(double);
+static_assert(SV_SMEM <= 232448 - 64, "shared memory per CTA");
+constexpr unsigned long long SV_NOT_YET = ~0ull;
+constexpr int SV_IP = 12, SV_INV_BLK = 8 * SV_IP;  // layout of the 8 x 8 inverse blocks (ldlt_device.cuh)
+
+struct SvArgs {
+  const double* K;
+  const double* Dg;
+  const double* Ginv;
+  double* x;
+  double* pub;    // exchange buffer of this sweep
+  double* reset;  // exchange buffer of the other sweep, re-armed here
+  int* ticket;
+  int ld, N, nblk;
+  long long* tlog;  // debug: [nblk][8] timestamps of this sweep (nullptr: off)
+};
+
+__device__ __forceinline__ long long sv_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// stamps are SM cycle counters (cheap); slot 7 holds one globaltimer reading taken together with
+// stamp 6 so that the per-SM counters can be put on a common time axis afterwards
+// (the __syncwarp re-converges warp 0: a diverged warp takes the slow path of every later shuffle)
+#define SV_STAMP(k) do { if (a.tlog) { if (tid == 0) a.tlog[(size_t)r * 16 + (k)] = clock64(); __syncwarp(); } } while (0)
+
+__device__ __forceinline__ void sv_cp16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(src_bytes));
+}
+
+__device__ __forceinline__ double sv_poll(const double* p) {
+  unsigned long long v;
+  long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    if (v != SV_NOT_YET) break;
+    if ((spin & 4095u) == 4095u) {  // watchdog: a protocol bug must not hang the device
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000LL) break;
+    }
+  }
+  return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void sv_publish(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(__double_as_longlong(v)) : "memory");
+}
+
+// sums v[0..15] over the warp; afterwards v[0] on lane l is the total of entry
+// 8*bit4(l) + 4*bit3(l) + 2*bit2(l) + bit1(l)
+__device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Packed lower-triangular storage of the prepared diagonal tile, COLUMN-major: column q (8-block
+// l = q / 8) holds rows 8l..127 contiguously, so the solve's access pattern (lane = row, all
+// lanes the same column) is bank-conflict free.
+__device__ __forceinline__ int sv_hc(int p, int q) {
+  const int l = q >> 3;
+  return 1024 * l - 32 * l * (l - 1) + (q & 7) * (SV_TB - 8 * l) + p - 8 * l;
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(SV_THREADS, 1) k_trsv_stream(SvArgs a) {
+  extern __shared__ __align__(16) double svm[];
+  double* ring = svm;
+  double* Hs = ring + SV_STAGES * SV_STAGE_DOUBLES;  // prepared diagonal tile
+  double* xs = Hs + SV_H_DOUBLES;                    // 2 x 128: x_j of the current / next tile
+  double* ts = xs + 2 * SV_TB;                       // 128: right-hand side of the diagonal step
+  double* xb = ts + SV_TB;                           // 2 x 8: block just solved
+  double* part = xb + 16;                            // 8 x 128 (backward: per-warp column sums)
+  __shared__ int s_tk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tk = atomicAdd(a.ticket, 1);
+  __syncthreads();
+  const int order = s_tk;
+  const int r = FWD ? order : a.nblk - 1 - order;
+  const int R0 = r * SV_TB, nr = min(SV_TB, a.N - R0);
+  const int ntiles = FWD ? r : a.nblk - 1 - r;
+  const int total = SV_SPT * ntiles;
+  if (tid < SV_TB) sv_publish(a.reset + R0 + tid, __longlong_as_double((long long)SV_NOT_YET));
+  SV_STAMP(0);
+
+  auto issue = [&](int st) {
+    const int t = st / SV_SPT, sl = st - t * SV_SPT;
+    double* dst = ring + (st % SV_STAGES) * SV_STAGE_DOUBLES;
+    const int j = FWD ? t : a.nblk - 1 - t;
+    const int row0 = (FWD ? R0 : j * SV_TB) + sl * SV_SR;
+    const double* base = a.K + (size_t)row0 * a.ld + (FWD ? j * SV_TB : R0);
+    const int row_lim = a.N - row0;
+#pragma unroll
+    for (int c = 0; c < SV_SR * SV_TB / 2 / SV_THREADS; ++c) {
+      const int idx = tid + c * SV_THREADS;
+      const int rr = idx >> 6, cc = (idx & 63) * 2;
+      const bool ok = rr < row_lim;
+      sv_cp16(dst + rr * SV_TB + cc, base + (size_t)(ok ? rr : 0) * a.ld + cc, ok ? 16 : 0);
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < SV_STAGES - 1; ++st) {
+    if (st < total) issue(st);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+
+  // ---- diagonal tile, prepared while the first tiles are in flight ----
+  // local index p: forward p = row; backward p = 127 - row (reversed transpose, again unit lower)
+  // strictly-lower 8 x 8 blocks: coalesced reads of the source rows, scattered into the packed layout
+  for (int sr = 8 + warp; sr < SV_TB; sr += SV_THREADS / 32) {
+    const int ncol = 8 * (sr >> 3);
+    const double* src = a.K + (size_t)(R0 + sr) * a.ld + R0;
+#pragma unroll
+    for (int c0 = 0; c0 < SV_TB - 8; c0 += 32) {
+      const int sc = c0 + lane;
+      if (sc < ncol) {
+        const double v = sr < nr ? src[sc] : 0.0;
+        const int p = FWD ? sr : SV_TB - 1 - sc, q = FWD ? sc : SV_TB - 1 - sr;
+        Hs[sv_hc(p, q)] = v;
+      }
+    }
+  }
+  // diagonal blocks: L_bb^-1 = D_b (D_b^-1 L_bb^-1), from the 8 x 8 inverse blocks of the factorization
+  for (int e = tid; e < SV_NBLK8 * 64; e += SV_THREADS) {
+    const int b = e >> 6, i = (e >> 3) & 7, c = e & 7;
+    double v = 0.0;
+    if (c <= i) {
+      const int gb = FWD ? b : SV_NBLK8 - 1 - b, gi = FWD ? i : 7 - c, gc = FWD ? c : 7 - i;
+      if (8 * gb + gi < nr)
+        v = a.Dg[R0 + 8 * gb + gi] * a.Ginv[(size_t)(R0 / 8 + gb) * SV_INV_BLK + gi * SV_IP + gc];
+    }
+    Hs[sv_hc(8 * b + i, 8 * b + c)] = v;
+  }
+  __syncthreads();
+  // H_{b,l} = L_bb^-1 L_{b,l}, in place: 8 threads (one per row) per block
+  {
+    const int grp = tid >> 3, i = tid & 7;
+    constexpr int NPAIR = SV_NBLK8 * (SV_NBLK8 - 1) / 2;
+    for (int pr0 = 0; pr0 < NPAIR; pr0 += SV_THREADS / 8) {
+      const int pr = pr0 + grp;
+      const bool on = pr < NPAIR;
+      int b = 1, l = 0;
+      if (on) {
+        while (b * (b + 1) / 2 <= pr) ++b;
+        l = pr - b * (b - 1) / 2;
+      }
+      double h[8];
+      if (on) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) h[c] = 0.0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const double li = Hs[sv_hc(8 * b + i, 8 * b + m)];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) h[c] = fma(li, Hs[sv_hc(8 * b + m, 8 * l + c)], h[c]);
+        }
+      }
+      __syncwarp();
+      if (on) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Hs[sv_hc(8 * b + i, 8 * l + c)] = h[c];
+      }
+      __syncwarp();
+    }
+  }
+
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+
+  // one 16 x 128 slice: forward  out[row] += sum_c S[row][c] x[c]  (lane owns columns 4*lane..+3, the
+  // warp 2 rows of the slice); backward  out[c] += sum_row S[row][c] x[row]
+  auto slice = [&](const double* S, int sl, const double2& x01, const double2& x23, const double* xv) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int rr = 2 * warp + i;
+      const double* rowp = S + rr * SV_TB + 4 * lane;
+      const double2 l01 = *reinterpret_cast<const double2*>(rowp);
+      const double2 l23 = *reinterpret_cast<const double2*>(rowp + 2);
+      if (FWD) {
+        double s2 = acc[sl * 2 + i];
+        s2 = fma(l01.x, x01.x, s2); s2 = fma(l01.y, x01.y, s2);
+        s2 = fma(l23.x, x23.x, s2); s2 = fma(l23.y, x23.y, s2);
+        acc[sl * 2 + i] = s2;
+      } else {
+        const double xr = xv[sl * SV_SR + rr];
+        acc[0] = fma(l01.x, xr, acc[0]); acc[1] = fma(l01.y, xr, acc[1]);
+        acc[2] = fma(l23.x, xr, acc[2]); acc[3] = fma(l23.y, xr, acc[3]);
+      }
+    }
+  };
+  // The critical section below (last tile, right-hand side, diagonal step, publish) is straight-line
+  // code that each CTA executes once: run cold it is dominated by instruction-cache misses (measured:
+  // 15k cycles cold vs ~3k warm).  So every CTA first runs it once on whatever is in shared memory with
+  // all side effects masked (pass 0) while it would be waiting for its inputs anyway.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  const bool real = pass != 0;
+  if (real) {
+    SV_STAMP(1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    for (int t = 0; t + 1 < ntiles; ++t) {
+      double* xv = xs + (t & 1) * SV_TB;
+      const int j = FWD ? t : a.nblk - 1 - t;
+      if (tid < SV_TB) xv[tid] = sv_poll(a.pub + (size_t)j * SV_TB + tid);
+#pragma unroll
+      for (int sl = 0; sl < SV_SPT; ++sl) {
+        const int st = SV_SPT * t + sl;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(SV_STAGES - 2));
+        __syncthreads();
+        if (st + SV_STAGES - 1 < total) issue(st + SV_STAGES - 1);
+        asm volatile("cp.async.commit_group;\n" ::);
+        const double2 x01 = *reinterpret_cast<const double2*>(xv + 4 * lane);
+        const double2 x23 = *reinterpret_cast<const double2*>(xv + 4 * lane + 2);
+        slice(ring + (st % SV_STAGES) * SV_STAGE_DOUBLES, sl, x01, x23, xv);
+      }
+    }
+  }
+  if (ntiles > 0) {
+    // last tile: nothing left to issue and all of it has landed -- one wait, one barrier
+    const int t = ntiles - 1;
+    double* xv = xs + (t & 1) * SV_TB;
+    if (real) {
+      const int j = FWD ? t : a.nblk - 1 - t;
+      SV_STAMP(2);
+      if (tid < SV_TB) xv[tid] = sv_poll(a.pub + (size_t)j * SV_TB + tid);
+      SV_STAMP(3);
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    if (real) SV_STAMP(4);
+    const double2 x01 = *reinterpret_cast<const double2*>(xv + 4 * lane);
+    const double2 x23 = *reinterpret_cast<const double2*>(xv + 4 * lane + 2);
+    int slot = (SV_SPT * t) % SV_STAGES;
+#pragma unroll
+    for (int sl = 0; sl < SV_SPT; ++sl) {
+      slice(ring + slot * SV_STAGE_DOUBLES, sl, x01, x23, xv);
+      slot = slot + 1 == SV_STAGES ? 0 : slot + 1;
+    }
+  }
+
+  // ---- right-hand side of the diagonal step, in local (possibly reversed) order ----
+  if (FWD) {
+    warp_reduce16(acc, lane);
+    const int e = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int row = SV_SR * (e >> 1) + 2 * warp + (e & 1);
+    if ((lane & 1) == 0) ts[row] = row < nr ? a.x[R0 + row] - acc[0] : 0.0;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[warp * SV_TB + 4 * lane + q] = acc[q];
+    __syncthreads();
+    if (tid < SV_TB) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s2 += part[w * SV_TB + tid];
+      ts[SV_TB - 1 - tid] = tid < nr ? a.x[R0 + tid] / a.Dg[R0 + tid] - s2 : 0.0;
+    }
+  }
+  __syncthreads();
+  if (real) SV_STAMP(5);
+
+  // ---- diagonal step: v = blockdiag(L_bb^-1) t, then v_i -= H[i][8b..8b+7] x_b block by block.
+  // Warp W (rows 32W..32W+31) finalises its four blocks with shuffles only; the 32 finished
+  // values cross to the later warps through shared memory once per warp (4 barriers, not 16).
+  if (tid < SV_TB) {
+    const int p = tid, pb = p >> 3, wq = p >> 5, lb = pb & 3;
+    double v = 0.0;
+    {
+      const double* tb = ts + 8 * pb;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v = fma(Hs[sv_hc(p, 8 * pb + c)], tb[c], v);
+    }
+    if (real) SV_STAMP(8);
+    double* xw = part;  // 4 x 32 finished values (the column sums of the backward sweep are consumed by now)
+    for (int W = 0; W < 4; ++W) {
+      if (wq == W) {
+        double h[24];
+#pragma unroll
+        for (int c = 0; c < 24; ++c) h[c] = (c >> 3) < lb ? Hs[sv_hc(p, 32 * W + c)] : 0.0;
+#pragma unroll
+        for (int sb = 0; sb < 3; ++sb) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            s0 = fma(h[8 * sb + c], __shfl_sync(0xffffffffu, v, 8 * sb + c), s0);
+            s1 = fma(h[8 * sb + c + 4], __shfl_sync(0xffffffffu, v, 8 * sb + c + 4), s1);
+          }
+          if (lb > sb) v -= s0 + s1;
+        }
+        xw[32 * W + lane] = v;
+        if (W == 0 && real) SV_STAMP(9);
+      }
+      double h[32];
+      if (wq > W) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) h[c] = Hs[sv_hc(p, 32 * W + c)];
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (real) SV_STAMP(10 + W);
+      if (wq > W) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double* xv = xw + 32 * W;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          s0 = fma(h[c], xv[c], s0);
+          s1 = fma(h[c + 8], xv[c + 8], s1);
+          s2 = fma(h[c + 16], xv[c + 16], s2);
+          s3 = fma(h[c + 24], xv[c + 24], s3);
+        }
+        v -= (s0 + s1) + (s2 + s3);
+      }
+    }
+    const int row = FWD ? p : SV_TB - 1 - p;
+    if (real) {
+      if (row < nr) a.x[R0 + row] = v;
+      sv_publish(a.pub + R0 + row, row < nr ? v : 0.0);
+    }
+  }
+  __syncthreads();  // pass 0: the scratch is re-used by pass 1
+  }  // pass
+  SV_STAMP(6);
+  if (a.tlog && tid == 0) a.tlog[(size_t)r * 16 + 7] = sv_now();
+  if (tid == 0 && order == a.nblk - 1) *a.ticket = 0;  // last ticket re-arms the counter for the next launch
+}
+
 }  // namespace
+
+int trsv_init() {
+  cudaError_t e = cudaFuncSetAttribute(k_trsv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_trsv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM);
+  return (int)e;
+}
+
+static long long* g_sv_log = nullptr;  // debug: device buffer [2][nblk][8]
+void trsv_set_debug_log(long long* dev) { g_sv_log = dev; }
 
 void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, const double* Dg, double* x,
                        size_t sx, TrsvWork& w) {
   if (fp.N <= 0 || fp.nslots <= 0) return;
+  static const int use_stream = getenv("IPMZ_TRSV_STREAM") ? atoi(getenv("IPMZ_TRSV_STREAM")) : 1;
+  if (use_stream && fp.df && fp.nslots == 1 && !fp.active) {
+    const DataflowPlan& p = *fp.df;
+    SvArgs v;
+    v.K = K; v.Dg = Dg; v.Ginv = fp.inv; v.x = x; v.ticket = p.solve_ticket;
+    v.ld = fp.ld; v.N = fp.N; v.nblk = p.nt;
+    double* fwd = p.xl;
+    double* bwd = p.xl + (size_t)p.nt * SV_TB;
+    v.pub = fwd; v.reset = bwd; v.tlog = g_sv_log;
+    k_trsv_stream<true><<<p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();
+    v.pub = bwd; v.reset = fwd; v.tlog = g_sv_log ? g_sv_log + (size_t)p.nt * 16 : nullptr;
+    k_trsv_stream<false><<<p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();
+    return;
+  }
   const int nblk = (fp.N + TB - 1) / TB;
   TrsvArgs a;
   a.K = K; a.Dg = Dg; a.x = x; a.ld = fp.ld; a.N = fp.N; a.nblk = nblk;
