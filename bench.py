@@ -233,21 +233,45 @@ def ours(args):
     value = world * args.steps * flops_step / (ms_max * 1e-3) * 1e-12
 
     prof = fac.profile()
+    info = fac.info()
     syrk_tf = prof["syrk_flops"] / (prof["syrk_ms"] * 1e-3) * 1e-12 if prof["syrk_ms"] > 0 else 0.0
     step_ms = ms_dev / args.steps
-    roofline = {
-        "bound": "tensor", "kernel": "k_syrk_ldl (FP64 DMMA trailing update)",
-        "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
-        "traffic": None,
-        "peak_source": "live DMMA issue-rate probe (ipmz_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 "
-                       "entry; cuBLAS DGEMM 8192^3 on this pool = 36.0 TFLOP/s (profiles/r01_fp64_ceilings.log)",
-        "flops_per_launch": prof["syrk_flops"] / max(1, prof["syrk_launches"]),
-        "launches_per_step": prof["syrk_launches"],
-        "ms_per_launch": prof["syrk_ms"] / max(1, prof["syrk_launches"]),
-        "share_of_step": prof["syrk_ms"] / step_ms if step_ms else None,
-        "diag_ms": prof["diag_ms"], "panel_ms": prof["panel_ms"], "syrk_ms": prof["syrk_ms"],
-        "whole_step_frac_of_peak": (flops_step / (step_ms * 1e-3) * 1e-12) / peak if peak else None,
-    }
+    factor_only_ms = fac.run(args.steps, 0) / args.steps
+    peak_src = ("live DMMA issue-rate probe (ipmz_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry; "
+                "cuBLAS DGEMM 8192^3 on this pool = 36.0 TFLOP/s (profiles/r01_fp64_ceilings.log)")
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
+        k = tj["k_ldlt_dataflow"]
+        if k["n"] == N and info["dataflow"]:
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        traffic = None
+    if info["dataflow"]:
+        # the whole factorization is ONE persistent kernel: algorithmic N^3/3 flops over its duration
+        roofline = {
+            "bound": "tensor", "kernel": "k_ldlt_dataflow (persistent dataflow LDL^T: DMMA tile updates + panel tasks)",
+            "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
+            "traffic": traffic, "traffic_unit": "DRAM bytes per launch (profiles/r01_traffic.json)",
+            "peak_source": peak_src,
+            "flops_per_launch": prof["syrk_flops"], "launches_per_step": 1,
+            "ms_per_launch": prof["syrk_ms"], "share_of_step": prof["syrk_ms"] / step_ms if step_ms else None,
+            "tasks_per_launch": info["ntasks"], "simulated_schedule_ms": info["simulated_us"] * 1e-3,
+            "factor_ms": factor_only_ms, "solves_ms": step_ms - factor_only_ms,
+            "whole_step_frac_of_peak": (flops_step / (step_ms * 1e-3) * 1e-12) / peak if peak else None,
+        }
+    else:
+        roofline = {
+            "bound": "tensor", "kernel": "k_syrk_ldl (FP64 DMMA trailing update)",
+            "achieved": syrk_tf, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tf / peak if peak else None,
+            "traffic": None, "peak_source": peak_src,
+            "flops_per_launch": prof["syrk_flops"] / max(1, prof["syrk_launches"]),
+            "launches_per_step": prof["syrk_launches"],
+            "ms_per_launch": prof["syrk_ms"] / max(1, prof["syrk_launches"]),
+            "share_of_step": prof["syrk_ms"] / step_ms if step_ms else None,
+            "diag_ms": prof["diag_ms"], "panel_ms": prof["panel_ms"], "syrk_ms": prof["syrk_ms"],
+            "whole_step_frac_of_peak": (flops_step / (step_ms * 1e-3) * 1e-12) / peak if peak else None,
+        }
     fac.close()
     del Kc
 

@@ -153,6 +153,14 @@ int ipmz_factor_run(ipmz_factor_handle h, int reps, int nrhs, double* ms_total);
  * diagonal-block, panel and trailing-update (DMMA) kernels; flops_syrk / n_syrk = algorithmic
  * flops and launch count of the trailing updates (the roofline numerator of bench.py). */
 int ipmz_factor_profile(ipmz_factor_handle h, double* ms3, double* flops_syrk, int* n_syrk);
+/* Which factorization path the handle runs: *dataflow = 1 for the persistent single-launch
+ * dataflow kernel (n >= IPMZ_DATAFLOW_MIN_N, default 2048), with its task count and the
+ * makespan of the host-simulated list schedule; 0 for the multi-kernel schedule. */
+int ipmz_factor_info(ipmz_factor_handle h, int* dataflow, int* ntasks, double* simulated_us);
+/* Host-only (no GPU needed): build the dataflow task list of an n x n matrix for `workers` SMs and
+ * check that it is a topological order covering every tile exactly once (the invariant that makes
+ * the device-side ticket queue deadlock-free).  counts3 = DIAG / TRSM / UPD tasks.  0 = valid. */
+int ipmz_schedule_check(int n, int workers, int* counts3, double* makespan_us, double* work_us);
 int ipmz_factor_get_solution(ipmz_factor_handle h, double* x_host);
 int ipmz_factor_get_ld(ipmz_factor_handle h, double* L_host, double* D_host);
 

@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_ldlt_decomposition", "ipmz_overwriting_solve_ldlt",
     "ipmz_factor_create", "ipmz_factor_destroy", "ipmz_factor_set_matrix", "ipmz_factor_set_rhs",
     "ipmz_factor_run", "ipmz_factor_profile", "ipmz_factor_get_solution", "ipmz_factor_get_ld",
+    "ipmz_factor_info", "ipmz_schedule_check",
     "ipmz_batch_create", "ipmz_batch_destroy", "ipmz_batch_upload", "ipmz_batch_solve",
     "ipmz_batch_get_iterates", "ipmz_batch_get_x",
 ]
@@ -351,6 +352,12 @@ class Factor:
         _check(lib().ipmz_factor_profile(self._h, _ptr(ms), C.byref(fl), C.byref(ns)))
         return dict(diag_ms=ms[0], panel_ms=ms[1], syrk_ms=ms[2], syrk_flops=fl.value, syrk_launches=ns.value)
 
+    def info(self):
+        """Factorization path of this handle: dict(dataflow, ntasks, simulated_us)."""
+        d, nt, us = C.c_int(), C.c_int(), C.c_double()
+        _check(lib().ipmz_factor_info(self._h, C.byref(d), C.byref(nt), C.byref(us)))
+        return dict(dataflow=bool(d.value), ntasks=nt.value, simulated_us=us.value)
+
     def solution(self):
         x = np.zeros(self.n)
         _check(lib().ipmz_factor_get_solution(self._h, _ptr(x)))
@@ -360,6 +367,15 @@ class Factor:
         L, D = np.zeros((self.n, self.n)), np.zeros(self.n)
         _check(lib().ipmz_factor_get_ld(self._h, _ptr(L), _ptr(D)))
         return L, D
+
+
+def schedule_check(n, workers=148):
+    """Host-only: the dataflow task list for an n x n matrix is a valid topological order.
+    Returns dict(valid, diag, trsm, upd, makespan_us, work_us)."""
+    cnt = (C.c_int * 3)()
+    mk, wk = C.c_double(), C.c_double()
+    rc = lib().ipmz_schedule_check(int(n), int(workers), cnt, C.byref(mk), C.byref(wk))
+    return dict(valid=rc == 0, diag=cnt[0], trsm=cnt[1], upd=cnt[2], makespan_us=mk.value, work_us=wk.value)
 
 
 def ldlt_decomposition(A):

@@ -51,7 +51,6 @@ struct DfArgs {
   double* W;
   double* Dg;
   double* Ginv;
-  double* Zinv;
   const int4* tasks;
   int* ticket;
   int* abort;
@@ -97,8 +96,6 @@ __device__ __forceinline__ void wait_deps(const DfArgs& a, const int4 tk, int la
   int want = 0;
   if (type == DF_DIAG) {
     if (lane == 0) { flag = a.cnt + (size_t)i * a.nt + j; want = j; }
-  } else if (type == DF_INV) {
-    if (lane == 0) { flag = a.rdy + (size_t)j * a.nt + j; want = 1; }
   } else if (type == DF_TRSM) {
     if (lane == 0) { flag = a.cnt + (size_t)i * a.nt + j; want = j; }
     if (lane == 1) { flag = a.rdy + (size_t)j * a.nt + j; want = 1; }
@@ -221,88 +218,6 @@ __device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i,
     }
 }
 
-
-// ---- INV(k): Z_k = L_kk^-1 of the unit-lower diagonal tile, in shared memory by recursive
-// doubling (Z21 = -Z22 L21 Z11 on the tensor pipe).  Only the triangular solves read Z_k: with it
-// the diagonal step of a block solve is a matrix-vector product instead of a 128-long
-// dependent substitution (trsv.cu).
-constexpr int TPI = 68;  // pitch of the L21 Z11 temporary
-__device__ __forceinline__ void df_inv_task(const DfArgs& a, double* sm, int k, int tid) {
-  double* S = sm;
-  double* T = sm + NB * SP;  // 64 x TPI
-  const int lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, q = lane & 3;
-  const int k0 = k * NB;
-  const int nb = min(NB, a.N - k0);
-  const double* Lkk = a.dst + (size_t)k0 * a.ld + k0;
-  for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
-  csync();
-  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, nb, nb, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  csync();
-  if (tid < NB) S[tid * SP + tid] = 1.0;  // unit diagonal (the factor stores the pivot there)
-  csync();
-  // 8 x 8 diagonal blocks: thread (b, j) forms column j of the inverse by forward substitution
-  double x[8];
-  if (tid < NB) {
-    const int b = tid >> 3, j = tid & 7;
-    const double* Lb = S + (8 * b) * SP + 8 * b;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < i) s += Lb[i * SP + c] * x[c];
-      if (i > j) x[i] = -s;
-    }
-  }
-  csync();
-  if (tid < NB) {
-    const int b = tid >> 3, j = tid & 7;
-    double* Lb = S + (8 * b) * SP + 8 * b;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i > j) Lb[i * SP + j] = x[i];
-  }
-  csync();
-  for (int h = 8; h < NB; h *= 2) {
-    const int hb = h >> 3, per = hb * hb, nblk = (NB / (2 * h)) * per;
-    // T_p = L21_p Z11_p
-    for (int blk = warp; blk < nblk; blk += DF_CONSUMERS) {
-      const int p = blk / per, rem = blk - p * per, bm = rem / hb, bn = rem - bm * hb;
-      const int base = p * 2 * h;
-      const double* A = S + (base + h + 8 * bm + g) * SP + base + q;
-      const double* B = S + (base + q) * SP + base + 8 * bn + g;
-      double acc[2] = {0.0, 0.0};
-      for (int kk = 0; kk < h; kk += 4) dmma884(acc, A[kk], B[kk * SP]);
-      double* t = T + (p * h + 8 * bm + g) * TPI + 8 * bn + 2 * q;
-      t[0] = acc[0];
-      t[1] = acc[1];
-    }
-    csync();
-    // Z21_p = -Z22_p T_p  (overwrites L21_p, which no later level reads)
-    for (int blk = warp; blk < nblk; blk += DF_CONSUMERS) {
-      const int p = blk / per, rem = blk - p * per, bm = rem / hb, bn = rem - bm * hb;
-      const int base = p * 2 * h;
-      const double* A = S + (base + h + 8 * bm + g) * SP + base + h + q;
-      const double* B = T + (p * h + q) * TPI + 8 * bn + g;
-      double acc[2] = {0.0, 0.0};
-      for (int kk = 0; kk < h; kk += 4) dmma884(acc, A[kk], B[kk * TPI]);
-      double* o = S + (base + h + 8 * bm + g) * SP + base + 8 * bn + 2 * q;
-      o[0] = -acc[0];
-      o[1] = -acc[1];
-    }
-    csync();
-  }
-  double* Z = a.Zinv + (size_t)k * NB * NB;
-  for (int idx = tid; idx < NB * NB / 2; idx += DF_CTHREADS) {
-    const int r = idx / (NB / 2), c = (idx - r * (NB / 2)) * 2;
-    *reinterpret_cast<double2*>(Z + (size_t)r * NB + c) = make_double2(S[r * SP + c], S[r * SP + c + 1]);
-  }
-}
 
 __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
   extern __shared__ __align__(16) double smem[];
@@ -484,10 +399,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
     } else {
       __syncthreads();  // producers have published and stopped touching the ring
       if (type == DF_DIAG) df_diag_task(a, smem, j, tid);
-      else if (type == DF_INV) df_inv_task(a, smem, j, tid);
       else df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid);
       csync();
-      if (tid == 0 && type != DF_INV) {
+      if (tid == 0) {
         __threadfence();
         if (type == DF_DIAG) st_release(a.rdy + (size_t)j * a.nt + j, 1);
         else red_release_add(a.rdy + (size_t)j * a.nt + i, 1);
@@ -521,6 +435,20 @@ static double env_double(const char* name, double dflt) {
   return s ? atof(s) : dflt;
 }
 
+bool dataflow_schedule_check(int N, int workers, int* counts3, double* makespan_us, double* work_us) {
+  DfModel m;
+  if (workers > 0) m.workers = workers;
+  const DfSchedule s = df_build_schedule(N, m);
+  if (counts3) {
+    counts3[0] = counts3[1] = counts3[2] = 0;
+    for (const DfTask& t : s.tasks)
+      if ((t.type & 0xff) <= DF_UPD) counts3[t.type & 0xff] += 1;
+  }
+  if (makespan_us) *makespan_us = s.makespan_us;
+  if (work_us) *work_us = s.work_us;
+  return df_validate_schedule(N, s);
+}
+
 int dataflow_min_n() { return env_int("IPMZ_DATAFLOW_MIN_N", 2048); }
 
 int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
@@ -538,7 +466,6 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   m.trsm_us = env_double("IPMZ_DF_TRSM_US", m.trsm_us);
   m.upd_base_us = env_double("IPMZ_DF_UPD_BASE_US", m.upd_base_us);
   m.upd_panel_us = env_double("IPMZ_DF_UPD_PANEL_US", m.upd_panel_us);
-  m.inv_us = env_double("IPMZ_DF_INV_US", m.inv_us);
   DfSchedule s = df_build_schedule(N, m);
   if (!df_validate_schedule(N, s)) return (int)cudaErrorInvalidValue;
   DataflowPlan* p = new DataflowPlan;
@@ -549,7 +476,6 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   if (e == cudaSuccess) e = cudaMalloc(&p->d_flags, sizeof(int) * p->flag_ints);
   if (e == cudaSuccess) e = cudaMalloc(&p->W, sizeof(double) * (size_t)N * ld);
   if (e == cudaSuccess) e = cudaMemset(p->W, 0, sizeof(double) * (size_t)N * ld);
-  if (e == cudaSuccess) e = cudaMalloc(&p->Zinv, sizeof(double) * (size_t)s.nt * NB * NB);
   if (e == cudaSuccess) e = cudaMalloc(&p->xl, sizeof(double) * 2 * (size_t)s.nt * NB);
   if (e == cudaSuccess) e = cudaMemset(p->xl, 0xff, sizeof(double) * 2 * (size_t)s.nt * NB);  // = the "not yet" pattern
   if (e == cudaSuccess) e = cudaMalloc(&p->solve_ticket, sizeof(int));
@@ -559,7 +485,7 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
     e = cudaMemcpy(p->d_tasks, s.tasks.data(), sizeof(int4) * s.tasks.size(), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
-    cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W); cudaFree(p->Zinv); cudaFree(p->xl);
+    cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W); cudaFree(p->xl);
     cudaFree(p->solve_ticket);
     delete p;
     return (int)e;
@@ -570,7 +496,7 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
 
 void dataflow_plan_destroy(DataflowPlan* p) {
   if (!p) return;
-  cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W); cudaFree(p->d_tlog); cudaFree(p->Zinv);
+  cudaFree(p->d_tasks); cudaFree(p->d_flags); cudaFree(p->W); cudaFree(p->d_tlog);
   cudaFree(p->xl); cudaFree(p->solve_ticket);
   delete p;
 }
@@ -582,7 +508,7 @@ static void df_launch(cudaStream_t st, const DataflowPlan& p, const double* src,
                       long long* tlog) {
   cudaMemsetAsync(p.d_flags, 0, sizeof(int) * p.flag_ints, st);
   DfArgs a;
-  a.src = src; a.dst = dst; a.W = p.W; a.Dg = Dg; a.Ginv = Ginv; a.Zinv = p.Zinv; a.tasks = p.d_tasks;
+  a.src = src; a.dst = dst; a.W = p.W; a.Dg = Dg; a.Ginv = Ginv; a.tasks = p.d_tasks;
   a.ticket = p.d_flags; a.abort = p.d_flags + 1; a.rdy = p.d_flags + 2; a.cnt = a.rdy + (size_t)p.nt * p.nt;
   a.tlog = tlog;
   a.N = p.N; a.ld = p.ld; a.nt = p.nt; a.ntasks = p.ntasks;

@@ -50,7 +50,6 @@ struct DataflowPlan {  // task list (host-simulated list schedule), dependency f
   int* d_flags = nullptr;  // [0] ticket, [1] abort, [2 ..) rdy[nt*nt], cnt[nt*nt]
   size_t flag_ints = 0;
   double* W = nullptr;     // N x ld, W = L D (pre-scaled B operand of the updates)
-  double* Zinv = nullptr;  // nt x 128 x 128, Z_k = L_kk^-1 (unit lower; identity-padded ragged tile)
   double* xl = nullptr;    // 2 x nt*128 self-validating exchange buffers of the solves (forward, backward)
   int* solve_ticket = nullptr;
   long long* d_tlog = nullptr;  // optional: 4 x ntasks (start ns, end ns, SM id, task words)
@@ -59,6 +58,8 @@ struct DataflowPlan {  // task list (host-simulated list schedule), dependency f
 int dataflow_init();
 int dataflow_min_n();  // matrices at least this large use the dataflow kernel (IPMZ_DATAFLOW_MIN_N; 0 = never)
 int dataflow_plan_create(DataflowPlan** out, int N, int ld);
+// host only: build + validate the task list (true = valid topological order covering every tile)
+bool dataflow_schedule_check(int N, int workers, int* counts3, double* makespan_us, double* work_us);
 void dataflow_plan_destroy(DataflowPlan* p);
 int dataflow_plan_ntasks(const DataflowPlan* p);
 double dataflow_plan_sim_us(const DataflowPlan* p);

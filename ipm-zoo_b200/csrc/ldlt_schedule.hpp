@@ -5,7 +5,6 @@
 //   DIAG(k)            LDL^T of the diagonal tile (k,k)                    after k updates of (k,k)
 //   TRSM(i,k,h)        64-row half h of tile (i,k):  X (D_k L_kk^T) = A    after DIAG(k) and k updates of (i,k)
 //   UPD(i,j,k0,k1)     C_ij -= sum_{k0<=k<k1} L_ik D_k L_jk^T              after TRSM(i,k), TRSM(j,k), cnt(i,j)==k0
-//   INV(k)             Z_k = L_kk^-1 (used by the triangular solves only)  after DIAG(k); nothing waits for it
 // The device kernel hands these out through ONE ticket counter, in the order of this list, and
 // each task spins on its dependencies (flags in global memory).  Any topological order is
 // deadlock-free (a waiting ticket only waits on lower tickets, all of which are held by running
@@ -27,7 +26,7 @@ namespace ipmz {
 constexpr int DF_TILE = 128;  // tile edge = panel width
 constexpr int DF_HALF = 64;   // rows per TRSM task
 
-enum DfType { DF_DIAG = 0, DF_TRSM = 1, DF_UPD = 2, DF_INV = 3, DF_DONE = 4 };
+enum DfType { DF_DIAG = 0, DF_TRSM = 1, DF_UPD = 2, DF_DONE = 3 };
 
 struct DfTask {
   int type;  // DfType | half << 8
@@ -41,8 +40,6 @@ struct DfModel {
   double trsm_us = 16.0;       // one 64-row half
   double upd_base_us = 7.0;    // C tile in/out + pipeline fill (measured: K=1 24.5 us, K=4 77 us)
   double upd_panel_us = 17.5;  // 128 x 128 x 128 on one SM at ~95 % of its DMMA rate
-  double inv_us = 25.0;        // inverse of one unit-lower 128 x 128 tile
-  bool with_inv = true;        // emit INV tasks (lowest priority: they fill idle SMs)
   int kb = 4;                  // panels accumulated before a non-urgent tile is updated
   int la = 2;                  // columns right of the chain front that are updated eagerly
   int kmax = 8;                // panels per UPD task at most (n=8192 sweep: kb 4 / kmax 8 best)
@@ -118,12 +115,10 @@ inline DfSchedule df_build_schedule(int N, const DfModel& m) {
   auto complete = [&](int idx) {
     const DfTask& tk = out.tasks[idx];
     const int type = tk.type & 0xff, i = tk.i, j = tk.j;
-    if (type == DF_INV) return;
     if (type == DF_DIAG) {
       diag_done[j] = 1;
       rdy[(size_t)j * nt + j] = 1;
       for (int r = j + 1; r < nt; ++r) touch(r, j);
-      if (m.with_inv) ready.push(Cand{key_of(nt + j, 3, j), DF_INV, j, j, 0});
     } else if (type == DF_TRSM) {
       rdy[(size_t)j * nt + i] += 1;
       if (panel_ready(j, i)) {
@@ -169,9 +164,6 @@ inline DfSchedule df_build_schedule(int N, const DfModel& m) {
       } else if (c.kind == DF_TRSM) {
         tk = DfTask{DF_TRSM | (c.h << 8), c.i, c.j, 0};
         dur = m.trsm_us;
-      } else if (c.kind == DF_INV) {
-        tk = DfTask{DF_INV, c.i, c.j, 0};
-        dur = m.inv_us;
       } else {
         tk = DfTask{DF_DIAG, c.i, c.j, 0};
         dur = m.diag_us;
@@ -203,8 +195,6 @@ inline bool df_validate_schedule(int N, const DfSchedule& s) {
   auto need_of = [&](int i) { return rows_of(i) > DF_HALF ? 2 : 1; };
   std::vector<int> rdy((size_t)nt * nt, 0), cnt((size_t)nt * nt, 0);
   std::vector<char> fin((size_t)nt * nt, 0);
-  std::vector<char> inv(nt, 0);
-  bool any_inv = false;
   for (const DfTask& tk : s.tasks) {
     const int type = tk.type & 0xff, i = tk.i, j = tk.j;
     if (i < j || i >= nt || j < 0) return false;
@@ -216,10 +206,6 @@ inline bool df_validate_schedule(int N, const DfSchedule& s) {
       if (i == j || !rdy[(size_t)j * nt + j] || cnt[(size_t)i * nt + j] != j) return false;
       if (++rdy[(size_t)j * nt + i] > need_of(i)) return false;
       fin[(size_t)i * nt + j] = 1;
-    } else if (type == DF_INV) {
-      if (i != j || !rdy[(size_t)j * nt + j] || inv[j]) return false;
-      inv[j] = 1;
-      any_inv = true;
     } else if (type == DF_UPD) {
       const int k0 = tk.k01 & 0xffff, k1 = tk.k01 >> 16;
       if (k0 >= k1 || k1 > j || cnt[(size_t)i * nt + j] != k0) return false;
@@ -232,7 +218,6 @@ inline bool df_validate_schedule(int N, const DfSchedule& s) {
   }
   for (int i = 0; i < nt; ++i)
     for (int j = 0; j <= i; ++j) {
-      if (any_inv && i == j && !inv[j]) return false;
       if (!fin[(size_t)i * nt + j]) return false;
       if (i != j && rdy[(size_t)j * nt + i] != need_of(i)) return false;
     }

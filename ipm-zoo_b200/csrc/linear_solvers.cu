@@ -224,6 +224,20 @@ int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double*
   return IPMZ_OK;
 }
 
+int ipmz_factor_info(ipmz_factor_handle h, int* dataflow, int* ntasks, double* simulated_us) {
+  if (!h) return ipmz_fail(IPMZ_ERR_ARG, "null argument");
+  if (dataflow) *dataflow = h->df ? 1 : 0;
+  if (ntasks) *ntasks = dataflow_plan_ntasks(h->df);
+  if (simulated_us) *simulated_us = dataflow_plan_sim_us(h->df);
+  return IPMZ_OK;
+}
+
+int ipmz_schedule_check(int n, int workers, int* counts3, double* makespan_us, double* work_us) {
+  if (n <= 0) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  return dataflow_schedule_check(n, workers, counts3, makespan_us, work_us) ? IPMZ_OK
+                                                                             : ipmz_fail(IPMZ_ERR_ARG, "invalid schedule");
+}
+
 int ipmz_debug_factor_timeline(ipmz_factor_handle h, double* out, int cap, int* nrec) {
   if (!h) return 1;
   if (ipmz_ensure_device(h->device)) return 2;

@@ -144,3 +144,36 @@ def test_batch_ragged_convergence(z):
         assert abs(res[i].f - tr.f[tr.iterations]) <= 1e-8 * max(1.0, abs(res[i].f))
     assert len(set(its)) > 1, "test needs differing iteration counts"
     bs.close()
+
+
+@pytest.mark.parametrize("n", [130, 257, 1000, 1536])
+def test_dataflow_path_ragged_sizes(n):
+    """The persistent dataflow factorization + streaming solves at sizes below their default
+    threshold (ragged last tile, 64-row half tiles), in a subprocess with IPMZ_DATAFLOW_MIN_N=128,
+    against numpy: factor residual, solve residual, and the quasi-definite sign pattern."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, ipm_zoo_b200 as z
+n = %d
+rng = np.random.default_rng(n)
+m = n // 3
+S = rng.standard_normal((n - m, n - m)) / np.sqrt(n)
+H = 2.0 * np.eye(n - m) + 0.5 * (S + S.T)
+A = rng.standard_normal((m, n - m)) / np.sqrt(n)
+K = np.block([[H, A.T], [A, -np.diag(rng.uniform(0.5, 2.0, m))]])
+f = z.Factor(n)
+assert f.info()["dataflow"], f.info()
+f.set_matrix(K); b = rng.standard_normal(n); f.set_rhs(b); f.run(1, 2)
+x = f.solution(); L, D = f.ld()
+v = rng.standard_normal(n)
+r1 = np.max(np.abs(K @ x - b)) / np.max(np.abs(b))
+r2 = np.max(np.abs(L @ (D * (L.T @ v)) - K @ v)) / np.max(np.abs(K @ v))
+assert r1 < 1e-11 and r2 < 1e-12, (r1, r2)
+assert np.all(D[:n - m] > 0) and np.all(D[n - m:] < 0)
+print("ok", r1, r2)
+''' % n
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IPMZ_DATAFLOW_MIN_N="128", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr

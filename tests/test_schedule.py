@@ -1,0 +1,51 @@
+"""Host logic of the persistent dataflow LDL^T (csrc/ldlt_schedule.hpp): the ticket order handed
+to the device must be a topological order of the tile DAG that covers every tile exactly once --
+that invariant is what makes the device-side spin-waits deadlock-free.  CPU only."""
+import numpy as np
+import pytest
+
+import ipm_zoo_b200 as z
+
+
+def expected_counts(n):
+    nt = (n + 127) // 128
+    rows = [min(128, n - 128 * i) for i in range(nt)]
+    halves = [2 if r > 64 else 1 for r in rows]
+    trsm = sum(halves[i] * i for i in range(nt))  # tile (i, k) for every k < i
+    return nt, trsm
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 128, 129, 192, 193, 256, 300, 1000, 2048, 3001, 4097, 8192])
+def test_schedule_is_valid_topological_order(n):
+    r = z.schedule_check(n)
+    assert r["valid"]
+    nt, trsm = expected_counts(n)
+    assert r["diag"] == nt and r["trsm"] == trsm
+    # every off-diagonal tile (i, j), j >= 1 and every diagonal tile j >= 1 receives >= 1 update task
+    assert r["upd"] >= nt * (nt - 1) // 2 if nt > 1 else r["upd"] == 0
+    assert r["work_us"] >= r["makespan_us"] > 0
+
+
+@pytest.mark.parametrize("workers", [1, 2, 7, 148, 1000])
+def test_schedule_valid_for_any_worker_count(workers):
+    for n in (129, 700, 2500):
+        r = z.schedule_check(n, workers)
+        assert r["valid"]
+        # one worker: the list schedule is serial, makespan = total modelled work
+        if workers == 1:
+            assert abs(r["makespan_us"] - r["work_us"]) < 1e-6 * r["work_us"]
+
+
+def test_schedule_scaling_model():
+    """More workers never make the simulated makespan worse by much, and the n=8192 plan keeps the
+    simulated machine >= 80 % busy (the look-ahead chain is hidden behind the bulk updates)."""
+    a = z.schedule_check(8192, 148)
+    assert a["valid"] and a["work_us"] / (a["makespan_us"] * 148) > 0.8
+    b = z.schedule_check(8192, 74)
+    assert b["makespan_us"] > a["makespan_us"]
+
+
+def test_random_sizes():
+    rng = np.random.default_rng(0)
+    for n in rng.integers(1, 6000, size=40):
+        assert z.schedule_check(int(n), int(rng.integers(1, 200)))["valid"]
