@@ -69,8 +69,37 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.nv, self.h, self.stop_flag, self.samples = None, None, False, []
+        try:  # NVML in-process: a sample every millisecond (the timed region is tens of ms)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].strip().isdigit() else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nv is not None:
+            self.stop_flag = False
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
@@ -86,6 +115,25 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            nv = self.nv
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            bits = 0
+            for x in self.samples:
+                bits |= int(x[1])
+            names = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                     ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                     ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")]
+            reasons = [nm for nm, attr in names if bits & int(getattr(nv, attr, 0))]
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                    "reasons": sorted(reasons), "how": "NVML polled every ms during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

@@ -193,7 +193,7 @@ constexpr int SV_TB = 128, SV_SR = 16, SV_SPT = SV_TB / SV_SR, SV_STAGES = SV_SP
 constexpr int SV_STAGE_DOUBLES = SV_SR * SV_TB;
 constexpr int SV_NBLK8 = SV_TB / 8;
 constexpr int SV_H_DOUBLES = 64 * (SV_NBLK8 * (SV_NBLK8 + 1) / 2);  // block-row packed lower triangle
-constexpr int SV_SMEM_DOUBLES = SV_STAGES * SV_STAGE_DOUBLES + SV_H_DOUBLES + 2 * SV_TB + SV_TB + 16 + 8 * SV_TB;
+constexpr int SV_SMEM_DOUBLES = SV_STAGES * SV_STAGE_DOUBLES + SV_H_DOUBLES + SV_TB + 8 * SV_TB;
 constexpr size_t SV_SMEM = (size_t)SV_SMEM_DOUBLES * sizeof(double);
 static_assert(SV_SMEM <= 232448 - 64, "shared memory per CTA");
 constexpr unsigned long long SV_NOT_YET = ~0ull;
@@ -203,12 +203,11 @@ struct SvArgs {
   const double* K;
   const double* Dg;
   const double* Ginv;
-  double* x;
-  double* pub;    // exchange buffer of this sweep
-  double* reset;  // exchange buffer of the other sweep, re-armed here
+  double* x;      // in: right-hand side, out: solution
+  double* xl;     // [2][nblk*128] exchange buffers: forward blocks y_r, backward blocks x_r
   int* ticket;
   int ld, N, nblk;
-  long long* tlog;  // debug: [nblk][8] timestamps of this sweep (nullptr: off)
+  long long* tlog;  // debug: [2][nblk][16] stamps (nullptr: off)
 };
 
 __device__ __forceinline__ long long sv_now() {
@@ -216,10 +215,6 @@ __device__ __forceinline__ long long sv_now() {
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
   return t;
 }
-// stamps are SM cycle counters (cheap); slot 7 holds one globaltimer reading taken together with
-// stamp 6 so that the per-SM counters can be put on a common time axis afterwards
-// (the __syncwarp re-converges warp 0: a diverged warp takes the slow path of every later shuffle)
-#define SV_STAMP(k) do { if (a.tlog) { if (tid == 0) a.tlog[(size_t)r * 16 + (k)] = clock64(); __syncwarp(); } } while (0)
 
 __device__ __forceinline__ void sv_cp16(void* smem_dst, const void* gsrc, int src_bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -233,13 +228,21 @@ __device__ __forceinline__ double sv_poll(const double* p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     if (v != SV_NOT_YET) break;
     if ((spin & 4095u) == 4095u) {  // watchdog: a protocol bug must not hang the device
-      long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+      const long long t = sv_now();
       if (t0 == 0) t0 = t;
       else if (t - t0 > 4000000000LL) break;
     }
   }
   return __longlong_as_double((long long)v);
+}
+// one non-blocking look (so that the looks at several chunks overlap); sv_poll_from continues from it
+__device__ __forceinline__ unsigned long long sv_peek(const double* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double sv_poll_from(unsigned long long v, const double* p) {
+  return v != SV_NOT_YET ? __longlong_as_double((long long)v) : sv_poll(p);
 }
 __device__ __forceinline__ void sv_publish(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(__double_as_longlong(v)) : "memory");
@@ -269,25 +272,26 @@ __device__ __forceinline__ int sv_hc(int p, int q) {
   return 1024 * l - 32 * l * (l - 1) + (q & 7) * (SV_TB - 8 * l) + p - 8 * l;
 }
 
+// One block row of one sweep.  FWD: y_r = L_rr^-1 (b_r - sum_{j<r} L_rj y_j), published only.
+// !FWD: x_r = L_rr^-T (y_r / D_r - sum_{j>r} L_jr^T x_j), published and written to a.x.
 template <bool FWD>
-__global__ void __launch_bounds__(SV_THREADS, 1) k_trsv_stream(SvArgs a) {
-  extern __shared__ __align__(16) double svm[];
+__device__ __forceinline__ void sv_block_row(const SvArgs& a, const int r, double* svm, const int tid) {
   double* ring = svm;
   double* Hs = ring + SV_STAGES * SV_STAGE_DOUBLES;  // prepared diagonal tile
-  double* xs = Hs + SV_H_DOUBLES;                    // 2 x 128: x_j of the current / next tile
-  double* ts = xs + 2 * SV_TB;                       // 128: right-hand side of the diagonal step
-  double* xb = ts + SV_TB;                           // 2 x 8: block just solved
-  double* part = xb + 16;                            // 8 x 128 (backward: per-warp column sums)
-  __shared__ int s_tk;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tk = atomicAdd(a.ticket, 1);
-  __syncthreads();
-  const int order = s_tk;
-  const int r = FWD ? order : a.nblk - 1 - order;
+  double* ts = Hs + SV_H_DOUBLES;                    // 128: right-hand side of the diagonal step
+  double* part = ts + SV_TB;                         // 8 x 128 (backward: per-warp column sums; then 4 x 32 finished x)
+  const int lane = tid & 31, warp = tid >> 5;
   const int R0 = r * SV_TB, nr = min(SV_TB, a.N - R0);
   const int ntiles = FWD ? r : a.nblk - 1 - r;
   const int total = SV_SPT * ntiles;
-  if (tid < SV_TB) sv_publish(a.reset + R0 + tid, __longlong_as_double((long long)SV_NOT_YET));
+  double* fwd = a.xl;
+  double* bwd = a.xl + (size_t)a.nblk * SV_TB;
+  double* pub = FWD ? fwd : bwd;
+  long long* tlog = a.tlog ? a.tlog + ((size_t)(FWD ? 0 : a.nblk) + r) * 16 : nullptr;
+// stamps are SM cycle counters; slot 7 holds one globaltimer reading taken together with stamp 6 so
+// that the per-SM counters can be put on a common time axis afterwards.  The __syncwarp
+// re-converges warp 0: a diverged warp takes the slow path of every later shuffle.
+#define SV_STAMP(k) do { if (tlog) { if (tid == 0) tlog[(k)] = clock64(); __syncwarp(); } } while (0)
   SV_STAMP(0);
 
   auto issue = [&](int st) {
@@ -371,176 +375,248 @@ __global__ void __launch_bounds__(SV_THREADS, 1) k_trsv_stream(SvArgs a) {
     }
   }
 
+  // Accumulators of the tile products.  Blocks of x arrive in four 32-entry chunks (the producer
+  // publishes each as soon as it is final), and a tile is consumed chunk by chunk:
+  //   forward   out[row] += sum_c S[row][c] x[c]:   chunk q = columns 32q..32q+31, lane = column within the
+  //             chunk, the warp owns rows 2*warp, 2*warp+1 of every 16-row slice -> acc[2*slice + i]
+  //   backward  out[c] += sum_row S[row][c] x[row]: chunk q = rows 32q..32q+31 = slices 2q, 2q+1, lane owns
+  //             columns 4*lane..+3 -> acc[0..3]; lane e < 16 fetches x[16*(e/2) + 2*warp + e%2] for its warp
   double acc[16];
+  // address this lane fetches of chunk q of the block at x_blk (backward: only lanes 4q..4q+3)
+  auto chunk_src = [&](const double* x_blk, int q) -> const double* {
+    return FWD ? x_blk + 32 * q + lane : x_blk + 16 * (lane >> 1) + 2 * warp + (lane & 1);
+  };
+  auto chunk = [&](const double* x_blk, int q, unsigned long long peeked, int slot0, bool real) {
+    if (FWD) {
+      const double xc = real ? sv_poll_from(peeked, chunk_src(x_blk, q)) : 0.0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-
-  // one 16 x 128 slice: forward  out[row] += sum_c S[row][c] x[c]  (lane owns columns 4*lane..+3, the
-  // warp 2 rows of the slice); backward  out[c] += sum_row S[row][c] x[row]
-  auto slice = [&](const double* S, int sl, const double2& x01, const double2& x23, const double* xv) {
+      for (int sl = 0; sl < SV_SPT; ++sl) {
+        int slot = slot0 + sl;
+        slot = slot >= SV_STAGES ? slot - SV_STAGES : slot;
+        const double* S = ring + slot * SV_STAGE_DOUBLES + (2 * warp) * SV_TB + 32 * q + lane;
+        acc[2 * sl] = fma(S[0], xc, acc[2 * sl]);
+        acc[2 * sl + 1] = fma(S[SV_TB], xc, acc[2 * sl + 1]);
+      }
+    } else {
+      double xm = 0.0;
+      if (real && (lane >> 2) == q) xm = sv_poll_from(peeked, chunk_src(x_blk, q));
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int rr = 2 * warp + i;
-      const double* rowp = S + rr * SV_TB + 4 * lane;
-      const double2 l01 = *reinterpret_cast<const double2*>(rowp);
-      const double2 l23 = *reinterpret_cast<const double2*>(rowp + 2);
-      if (FWD) {
-        double s2 = acc[sl * 2 + i];
-        s2 = fma(l01.x, x01.x, s2); s2 = fma(l01.y, x01.y, s2);
-        s2 = fma(l23.x, x23.x, s2); s2 = fma(l23.y, x23.y, s2);
-        acc[sl * 2 + i] = s2;
-      } else {
-        const double xr = xv[sl * SV_SR + rr];
-        acc[0] = fma(l01.x, xr, acc[0]); acc[1] = fma(l01.y, xr, acc[1]);
-        acc[2] = fma(l23.x, xr, acc[2]); acc[3] = fma(l23.y, xr, acc[3]);
+      for (int h = 0; h < 2; ++h) {
+        const int sl = 2 * q + h;
+        int slot = slot0 + sl;
+        slot = slot >= SV_STAGES ? slot - SV_STAGES : slot;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double xr = __shfl_sync(0xffffffffu, xm, 2 * sl + i);
+          const double* rowp = ring + slot * SV_STAGE_DOUBLES + (2 * warp + i) * SV_TB + 4 * lane;
+          const double2 l01 = *reinterpret_cast<const double2*>(rowp);
+          const double2 l23 = *reinterpret_cast<const double2*>(rowp + 2);
+          acc[0] = fma(l01.x, xr, acc[0]); acc[1] = fma(l01.y, xr, acc[1]);
+          acc[2] = fma(l23.x, xr, acc[2]); acc[3] = fma(l23.y, xr, acc[3]);
+        }
       }
     }
   };
+
   // The critical section below (last tile, right-hand side, diagonal step, publish) is straight-line
-  // code that each CTA executes once: run cold it is dominated by instruction-cache misses (measured:
-  // 15k cycles cold vs ~3k warm).  So every CTA first runs it once on whatever is in shared memory with
-  // all side effects masked (pass 0) while it would be waiting for its inputs anyway.
+  // code that each CTA executes once: run cold it is dominated by instruction-cache misses.  So every
+  // CTA first runs it once on whatever is in shared memory with all side effects masked (pass 0)
+  // while it would be waiting for its inputs anyway.
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-  const bool real = pass != 0;
-  if (real) {
-    SV_STAMP(1);
+    const bool real = pass != 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-    for (int t = 0; t + 1 < ntiles; ++t) {
-      double* xv = xs + (t & 1) * SV_TB;
-      const int j = FWD ? t : a.nblk - 1 - t;
-      if (tid < SV_TB) xv[tid] = sv_poll(a.pub + (size_t)j * SV_TB + tid);
-#pragma unroll
-      for (int sl = 0; sl < SV_SPT; ++sl) {
-        const int st = SV_SPT * t + sl;
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(SV_STAGES - 2));
-        __syncthreads();
-        if (st + SV_STAGES - 1 < total) issue(st + SV_STAGES - 1);
-        asm volatile("cp.async.commit_group;\n" ::);
-        const double2 x01 = *reinterpret_cast<const double2*>(xv + 4 * lane);
-        const double2 x23 = *reinterpret_cast<const double2*>(xv + 4 * lane + 2);
-        slice(ring + (st % SV_STAGES) * SV_STAGE_DOUBLES, sl, x01, x23, xv);
+    // right-hand side entry of this thread's row, fetched before the tiles so that its latency is hidden
+    // (forward: b; backward: the forward result of this block row over the pivot)
+    double rhs_val = 0.0;
+    if (real) {
+      if (FWD) {
+        const int e = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        const int row = SV_SR * (e >> 1) + 2 * warp + (e & 1);
+        if (row < nr) rhs_val = a.x[R0 + row];
+      } else if (tid < nr) {
+        rhs_val = sv_poll(fwd + R0 + tid) / a.Dg[R0 + tid];
       }
     }
-  }
-  if (ntiles > 0) {
-    // last tile: nothing left to issue and all of it has landed -- one wait, one barrier
-    const int t = ntiles - 1;
-    double* xv = xs + (t & 1) * SV_TB;
     if (real) {
-      const int j = FWD ? t : a.nblk - 1 - t;
-      SV_STAMP(2);
-      if (tid < SV_TB) xv[tid] = sv_poll(a.pub + (size_t)j * SV_TB + tid);
-      SV_STAMP(3);
-      asm volatile("cp.async.wait_group 0;\n" ::);
-    }
-    __syncthreads();
-    if (real) SV_STAMP(4);
-    const double2 x01 = *reinterpret_cast<const double2*>(xv + 4 * lane);
-    const double2 x23 = *reinterpret_cast<const double2*>(xv + 4 * lane + 2);
-    int slot = (SV_SPT * t) % SV_STAGES;
+      SV_STAMP(1);
+      for (int t = 0; t + 1 < ntiles; ++t) {  // streaming tiles: their x blocks were published long ago
+        const int j = FWD ? t : a.nblk - 1 - t;
+        const double* x_blk = pub + (size_t)j * SV_TB;
+        double xq[4];
+        if (FWD) {
 #pragma unroll
-    for (int sl = 0; sl < SV_SPT; ++sl) {
-      slice(ring + slot * SV_STAGE_DOUBLES, sl, x01, x23, xv);
-      slot = slot + 1 == SV_STAGES ? 0 : slot + 1;
-    }
-  }
-
-  // ---- right-hand side of the diagonal step, in local (possibly reversed) order ----
-  if (FWD) {
-    warp_reduce16(acc, lane);
-    const int e = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    const int row = SV_SR * (e >> 1) + 2 * warp + (e & 1);
-    if ((lane & 1) == 0) ts[row] = row < nr ? a.x[R0 + row] - acc[0] : 0.0;
-  } else {
+          for (int q = 0; q < 4; ++q) xq[q] = sv_poll(x_blk + 32 * q + lane);
+        } else {
+          xq[0] = lane < 16 ? sv_poll(x_blk + 16 * (lane >> 1) + 2 * warp + (lane & 1)) : 0.0;
+        }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) part[warp * SV_TB + 4 * lane + q] = acc[q];
-    __syncthreads();
-    if (tid < SV_TB) {
-      double s2 = 0.0;
+        for (int sl = 0; sl < SV_SPT; ++sl) {
+          const int st = SV_SPT * t + sl;
+          asm volatile("cp.async.wait_group %0;\n" ::"n"(SV_STAGES - 2));
+          __syncthreads();
+          if (st + SV_STAGES - 1 < total) issue(st + SV_STAGES - 1);
+          asm volatile("cp.async.commit_group;\n" ::);
+          const double* S = ring + (st % SV_STAGES) * SV_STAGE_DOUBLES + (2 * warp) * SV_TB;
+          if (FWD) {
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s2 += part[w * SV_TB + tid];
-      ts[SV_TB - 1 - tid] = tid < nr ? a.x[R0 + tid] / a.Dg[R0 + tid] - s2 : 0.0;
-    }
-  }
-  __syncthreads();
-  if (real) SV_STAMP(5);
-
-  // ---- diagonal step: v = blockdiag(L_bb^-1) t, then v_i -= H[i][8b..8b+7] x_b block by block.
-  // Warp W (rows 32W..32W+31) finalises its four blocks with shuffles only; the 32 finished
-  // values cross to the later warps through shared memory once per warp (4 barriers, not 16).
-  if (tid < SV_TB) {
-    const int p = tid, pb = p >> 3, wq = p >> 5, lb = pb & 3;
-    double v = 0.0;
-    {
-      const double* tb = ts + 8 * pb;
+            for (int q = 0; q < 4; ++q) {
+              acc[2 * sl] = fma(S[32 * q + lane], xq[q], acc[2 * sl]);
+              acc[2 * sl + 1] = fma(S[SV_TB + 32 * q + lane], xq[q], acc[2 * sl + 1]);
+            }
+          } else {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v = fma(Hs[sv_hc(p, 8 * pb + c)], tb[c], v);
-    }
-    if (real) SV_STAMP(8);
-    double* xw = part;  // 4 x 32 finished values (the column sums of the backward sweep are consumed by now)
-    for (int W = 0; W < 4; ++W) {
-      if (wq == W) {
-        double h[24];
-#pragma unroll
-        for (int c = 0; c < 24; ++c) h[c] = (c >> 3) < lb ? Hs[sv_hc(p, 32 * W + c)] : 0.0;
-#pragma unroll
-        for (int sb = 0; sb < 3; ++sb) {
-          double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            s0 = fma(h[8 * sb + c], __shfl_sync(0xffffffffu, v, 8 * sb + c), s0);
-            s1 = fma(h[8 * sb + c + 4], __shfl_sync(0xffffffffu, v, 8 * sb + c + 4), s1);
+            for (int i = 0; i < 2; ++i) {
+              const double xr = __shfl_sync(0xffffffffu, xq[0], 2 * sl + i);
+              const double2 l01 = *reinterpret_cast<const double2*>(S + i * SV_TB + 4 * lane);
+              const double2 l23 = *reinterpret_cast<const double2*>(S + i * SV_TB + 4 * lane + 2);
+              acc[0] = fma(l01.x, xr, acc[0]); acc[1] = fma(l01.y, xr, acc[1]);
+              acc[2] = fma(l23.x, xr, acc[2]); acc[3] = fma(l23.y, xr, acc[3]);
+            }
           }
-          if (lb > sb) v -= s0 + s1;
         }
-        xw[32 * W + lane] = v;
-        if (W == 0 && real) SV_STAMP(9);
-      }
-      double h[32];
-      if (wq > W) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) h[c] = Hs[sv_hc(p, 32 * W + c)];
-      }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (real) SV_STAMP(10 + W);
-      if (wq > W) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        const double* xv = xw + 32 * W;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          s0 = fma(h[c], xv[c], s0);
-          s1 = fma(h[c + 8], xv[c + 8], s1);
-          s2 = fma(h[c + 16], xv[c + 16], s2);
-          s3 = fma(h[c + 24], xv[c + 24], s3);
-        }
-        v -= (s0 + s1) + (s2 + s3);
       }
     }
-    const int row = FWD ? p : SV_TB - 1 - p;
-    if (real) {
-      if (row < nr) a.x[R0 + row] = v;
-      sv_publish(a.pub + R0 + row, row < nr ? v : 0.0);
+    if (ntiles > 0) {
+      // last tile: nothing left to issue and all of it has landed -- one wait, one barrier, then chunk by chunk
+      const int t = ntiles - 1;
+      const int j = FWD ? t : a.nblk - 1 - t;
+      if (real) {
+        SV_STAMP(2);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      }
+      __syncthreads();
+      const int slot0 = (SV_SPT * t) % SV_STAGES;
+      const double* x_blk = pub + (size_t)j * SV_TB;
+      // chunks in the order the producer publishes them (its warp 0 first: forward rows 0..31,
+      // backward rows 127..96); one look at all four first, so that their round trips overlap
+      unsigned long long pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pk[q] = (real && (FWD || (lane >> 2) == q)) ? sv_peek(chunk_src(x_blk, q)) : SV_NOT_YET;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = FWD ? k : 3 - k;
+        chunk(x_blk, q, pk[q], slot0, real);
+        if (real && k == 0) SV_STAMP(8);
+        if (real && k == 1) SV_STAMP(9);
+        if (real && k == 2) SV_STAMP(3);
+      }
+      if (real) SV_STAMP(4);
     }
-  }
-  __syncthreads();  // pass 0: the scratch is re-used by pass 1
+
+    // ---- right-hand side of the diagonal step, in local (possibly reversed) order ----
+    if (FWD) {
+      warp_reduce16(acc, lane);
+      const int e = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const int row = SV_SR * (e >> 1) + 2 * warp + (e & 1);
+      if ((lane & 1) == 0) ts[row] = row < nr ? rhs_val - acc[0] : 0.0;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part[warp * SV_TB + 4 * lane + q] = acc[q];
+      __syncthreads();
+      if (tid < SV_TB) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s2 += part[w * SV_TB + tid];
+        ts[SV_TB - 1 - tid] = tid < nr ? rhs_val - s2 : 0.0;
+      }
+    }
+    __syncthreads();
+    if (real) SV_STAMP(5);
+
+    // ---- diagonal step: v = blockdiag(L_bb^-1) t, then v_i -= H[i][8b..8b+7] x_b block by block.
+    // Warp W (rows 32W..32W+31) finalises its four blocks with shuffles only and publishes them at
+    // once; the 32 finished values cross to the later warps through shared memory (4 barriers, not 16).
+    if (tid < SV_TB) {
+      const int p = tid, pb = p >> 3, wq = p >> 5, lb = pb & 3;
+      const int row = FWD ? p : SV_TB - 1 - p;
+      double v = 0.0;
+      {
+        const double* tb = ts + 8 * pb;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v = fma(Hs[sv_hc(p, 8 * pb + c)], tb[c], v);
+      }
+      double* xw = part;  // the column sums of the backward sweep are consumed by now
+      for (int W = 0; W < 4; ++W) {
+        if (wq == W) {
+          double h[24];
+#pragma unroll
+          for (int c = 0; c < 24; ++c) h[c] = (c >> 3) < lb ? Hs[sv_hc(p, 32 * W + c)] : 0.0;
+#pragma unroll
+          for (int sb = 0; sb < 3; ++sb) {
+            // block sb of this warp is final: broadcast its 8 values through shared memory
+            if (lb == sb) xw[32 * W + lane] = v;
+            __syncwarp();
+            const double2 b01 = *reinterpret_cast<const double2*>(xw + 32 * W + 8 * sb);
+            const double2 b23 = *reinterpret_cast<const double2*>(xw + 32 * W + 8 * sb + 2);
+            const double2 b45 = *reinterpret_cast<const double2*>(xw + 32 * W + 8 * sb + 4);
+            const double2 b67 = *reinterpret_cast<const double2*>(xw + 32 * W + 8 * sb + 6);
+            double s0 = h[8 * sb] * b01.x, s1 = h[8 * sb + 4] * b45.x;
+            s0 = fma(h[8 * sb + 1], b01.y, s0); s1 = fma(h[8 * sb + 5], b45.y, s1);
+            s0 = fma(h[8 * sb + 2], b23.x, s0); s1 = fma(h[8 * sb + 6], b67.x, s1);
+            s0 = fma(h[8 * sb + 3], b23.y, s0); s1 = fma(h[8 * sb + 7], b67.y, s1);
+            if (lb > sb) v -= s0 + s1;
+          }
+          if (real) {
+            sv_publish(pub + R0 + row, row < nr ? v : 0.0);
+            if (!FWD && row < nr) a.x[R0 + row] = v;
+          }
+          if (lb == 3) xw[32 * W + lane] = v;
+        }
+        double h[32];
+        if (wq > W) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) h[c] = Hs[sv_hc(p, 32 * W + c)];
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (real) SV_STAMP(10 + W);
+        if (wq > W) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          const double* xv = xw + 32 * W;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            s0 = fma(h[c], xv[c], s0);
+            s1 = fma(h[c + 8], xv[c + 8], s1);
+            s2 = fma(h[c + 16], xv[c + 16], s2);
+            s3 = fma(h[c + 24], xv[c + 24], s3);
+          }
+          v -= (s0 + s1) + (s2 + s3);
+        }
+      }
+    }
+    __syncthreads();  // pass 0: the scratch is re-used by pass 1
   }  // pass
   SV_STAMP(6);
-  if (a.tlog && tid == 0) a.tlog[(size_t)r * 16 + 7] = sv_now();
-  if (tid == 0 && order == a.nblk - 1) *a.ticket = 0;  // last ticket re-arms the counter for the next launch
+  if (tlog && tid == 0) tlog[7] = sv_now();
+#undef SV_STAMP
+}
+
+// Both sweeps of one solve in ONE launch: tickets 0..nblk-1 are the forward block rows in order,
+// tickets nblk..2nblk-1 the backward block rows from the last to the first.  A ticket only ever
+// waits on lower tickets, so any number of CTAs may be resident.  The backward CTAs prepare their
+// diagonal tiles and prefetch their first tiles while the forward sweep is still running.
+__global__ void __launch_bounds__(SV_THREADS, 1) k_trsv_fused(SvArgs a) {
+  extern __shared__ __align__(16) double svm[];
+  __shared__ int s_tk;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_tk = atomicAdd(a.ticket, 1);
+  __syncthreads();
+  const int order = s_tk;
+  if (order < a.nblk) sv_block_row<true>(a, order, svm, tid);
+  else sv_block_row<false>(a, 2 * a.nblk - 1 - order, svm, tid);
+  if (tid == 0 && order == 2 * a.nblk - 1) *a.ticket = 0;  // last ticket re-arms the counter for the next launch
 }
 
 }  // namespace
 
 int trsv_init() {
-  cudaError_t e = cudaFuncSetAttribute(k_trsv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_trsv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM);
-  return (int)e;
+  return (int)cudaFuncSetAttribute(k_trsv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM);
 }
 
-static long long* g_sv_log = nullptr;  // debug: device buffer [2][nblk][8]
+static long long* g_sv_log = nullptr;  // debug: device buffer [2][nblk][16]
 void trsv_set_debug_log(long long* dev) { g_sv_log = dev; }
 
 void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, const double* Dg, double* x,
@@ -550,14 +626,10 @@ void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, c
   if (use_stream && fp.df && fp.nslots == 1 && !fp.active) {
     const DataflowPlan& p = *fp.df;
     SvArgs v;
-    v.K = K; v.Dg = Dg; v.Ginv = fp.inv; v.x = x; v.ticket = p.solve_ticket;
-    v.ld = fp.ld; v.N = fp.N; v.nblk = p.nt;
-    double* fwd = p.xl;
-    double* bwd = p.xl + (size_t)p.nt * SV_TB;
-    v.pub = fwd; v.reset = bwd; v.tlog = g_sv_log;
-    k_trsv_stream<true><<<p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();
-    v.pub = bwd; v.reset = fwd; v.tlog = g_sv_log ? g_sv_log + (size_t)p.nt * 16 : nullptr;
-    k_trsv_stream<false><<<p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();
+    v.K = K; v.Dg = Dg; v.Ginv = fp.inv; v.x = x; v.xl = p.xl; v.ticket = p.solve_ticket;
+    v.ld = fp.ld; v.N = fp.N; v.nblk = p.nt; v.tlog = g_sv_log;
+    cudaMemsetAsync(p.xl, 0xff, sizeof(double) * 2 * (size_t)p.nt * SV_TB, st);  // every entry "not yet"
+    k_trsv_fused<<<2 * p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();
     return;
   }
   const int nblk = (fp.N + TB - 1) / TB;
