@@ -33,13 +33,16 @@ namespace ipmz {
 namespace {
 
 constexpr int DF_STAGES = 5;
-constexpr int DF_CONSUMERS = 16, DF_PRODUCERS = 4;
+constexpr int DF_CONSUMERS = 8, DF_PRODUCERS = 4;
+constexpr int DF_MI = 8, DF_NI = 4;  // consumer warp tile = 64 x 32 (2 x 4 warps)
+constexpr int DF_CONSUMER_REGS = 232, DF_PRODUCER_REGS = 40;
+constexpr int DF_LAG = 2;  // k-slices consumer group 1 trails group 0 (<= DF_STAGES - 2)  // setmaxnreg after the role split
 constexpr int DF_CTHREADS = DF_CONSUMERS * 32;
 constexpr int DF_PTHREADS = DF_PRODUCERS * 32;
 constexpr int DF_THREADS = DF_CTHREADS + DF_PTHREADS;
 constexpr int DF_STAGE_DOUBLES = 2 * DF_TILE * LDT;
 constexpr int DF_RING_DOUBLES = DF_STAGES * DF_STAGE_DOUBLES;
-constexpr int DF_BULK_DOUBLES = NB * SP + RB * SP + 2 * NB + 2 * SB + 16 * 96;
+constexpr int DF_BULK_DOUBLES = NB * SP + RB * SP + 2 * NB + CBUF + 16 * 96;
 constexpr int DF_DATA_DOUBLES = DF_RING_DOUBLES > DF_BULK_DOUBLES ? DF_RING_DOUBLES : DF_BULK_DOUBLES;
 constexpr size_t DF_SMEM = (size_t)DF_DATA_DOUBLES * sizeof(double) + 256;
 static_assert(DF_TILE == NB && DF_HALF == RB, "tile grid of the schedule = panel geometry of the kernels");
@@ -127,27 +130,36 @@ __device__ __forceinline__ void wait_deps(const DfArgs& a, const int4 tk, int la
 }
 
 // ---- DIAG(k): LDL^T of the diagonal tile, 16 consumer warps (body of k_diag_ldlt, factor.cu) ----
-__device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k, int tid) {
+__device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k, int tid, long long* ph) {
   double* S = sm;
   double* dsm = sm + NB * SP + RB * SP;
   double* dinv = dsm + NB;
   double* colbuf = dinv + NB;
-  double* binv = colbuf + 2 * SB;
+  double* binv = colbuf + CBUF;
   const int lane = tid & 31, warp = tid >> 5;
   const int k0 = k * NB;
   const int nb = min(NB, a.N - k0);
   const double* A = (k == 0 ? a.src : a.dst) + (size_t)k0 * a.ld + k0;
   double* O = a.dst + (size_t)k0 * a.ld + k0;
 
-  for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
-  csync();
+  const long long c_begin = ph ? clock64() : 0;
+  long long c_ldlt = 0;
+  if (nb < NB) {  // ragged tile: partial sub-blocks must not read uninitialised shared memory
+    for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
+    csync();
+  }
   async_block_load<true, DF_CTHREADS>(S, A, a.ld, nb, nb, tid);
   cp_async_commit();
   cp_async_wait<0>();
   csync();
+  const long long c_loaded = ph ? clock64() : 0;
   for (int j0 = 0; j0 < nb; j0 += SB) {
     const int jb = min(SB, nb - j0);
-    if (warp == 0) warp_ldlt32(S, j0, jb, dsm, dinv, colbuf, binv + (j0 / SB) * INV_SUB, lane);
+    if (warp == 0) {
+      const long long c0 = ph ? clock64() : 0;
+      warp_ldlt32(S, j0, jb, dsm, dinv, colbuf, binv + (j0 / SB) * INV_SUB, lane);
+      if (ph) c_ldlt += clock64() - c0;
+    }
     csync();
     const int base = j0 + jb, rem = nb - base;
     if (rem > 0) {
@@ -159,11 +171,18 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
       csync();
     }
   }
+  const long long c_factored = ph ? clock64() : 0;
   for (int r = warp; r < nb; r += DF_CONSUMERS) {
     for (int c = lane; c < r; c += 32) O[(size_t)r * a.ld + c] = S[r * SP + c];
     if (lane == 0) O[(size_t)r * a.ld + r] = dsm[r];
   }
   for (int t = tid; t < nb; t += DF_CTHREADS) a.Dg[k0 + t] = dsm[t];
+  if (ph && tid == 0) {
+    ph[0] = c_loaded - c_begin;       // load
+    ph[1] = c_ldlt;                   // the four one-warp 32 x 32 factorizations
+    ph[2] = c_factored - c_loaded;    // whole elimination loop
+    ph[3] = clock64() - c_factored;   // store (issue)
+  }
   {
     double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
     const int nblk = (nb + SB - 1) / SB * 4;
@@ -171,51 +190,96 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
   }
 }
 
-// ---- TRSM(i,k,h): 64 rows of the panel below the diagonal tile (body of k_trsm_panel) ----
-__device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i, int k, int h, int tid) {
+// ---- TRSM(i,k,h): 64 rows of the panel below the diagonal tile,  X (D L_kk^T) = A ----
+// Register-resident: every warp keeps its 8 x 128 row block as 16 DMMA accumulator fragments and
+// sweeps the 8-column blocks left to right with no block-level synchronisation:
+//   X_b = R_b Binv_b^T                      (Binv_b = D_b^-1 L_bb^-1, the 8 x 8 inverse blocks of DIAG)
+//   R_b' -= (X_b D_b) L_b'b^T   for b' > b   (independent accumulators: the tensor pipe stays full)
+// Only L_kk sits in shared memory (B fragments); accumulator -> A-fragment conversion is a
+// shuffle inside each quad.  FP64 work 64 x 128^2 / 2 FMA = 8.2k cycles on one SM's DMMA pipe.
+__device__ __forceinline__ double quad_afrag(const double (&c)[2], int src, int odd, unsigned) {
+  const double v0 = __shfl_sync(0xffffffffu, c[0], src);
+  const double v1 = __shfl_sync(0xffffffffu, c[1], src);
+  return odd ? v1 : v0;
+}
+__device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i, int k, int h, int tid, long long* ph) {
   double* S = sm;
-  double* T = sm + NB * SP;
-  double* dsm = T + RB * SP;
-  double* binv = dsm + 2 * NB + 2 * SB;
+  double* dsm = sm + NB * SP + RB * SP;
+  double* binv = dsm + 2 * NB + CBUF;
   const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
   const int k0 = k * NB;
-  const int nb = NB;  // a panel with rows below it is always full width
   const int r0 = i * DF_TILE + h * RB;
-  const int nr = min(RB, a.N - r0);
   const double* Lkk = a.dst + (size_t)k0 * a.ld + k0;
   const double* Ain = (k == 0 ? a.src : a.dst) + (size_t)r0 * a.ld + k0;
   double* Aout = a.dst + (size_t)r0 * a.ld + k0;
+  double* Wout = a.W + (size_t)r0 * a.ld + k0;
 
-  if (nr < RB) {
-    for (int t = tid; t < RB * SP; t += DF_CTHREADS) T[t] = 0.0;
-    csync();
-  }
-  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, nb, nb, tid);
-  async_block_load<false, DF_CTHREADS>(T, Ain, a.ld, nr, nb, tid);
+  const long long c_begin = ph ? clock64() : 0;
+  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, NB, NB, tid);
   cp_async_commit();
-  for (int t = tid; t < nb; t += DF_CTHREADS) dsm[t] = __ldcg(a.Dg + k0 + t);
+  const long long c_issued = ph ? clock64() : 0;
+  for (int t = tid; t < NB; t += DF_CTHREADS) dsm[t] = __ldcg(a.Dg + k0 + t);
   {
     const double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
     for (int t = tid; t < 16 * INV_BLK; t += DF_CTHREADS) binv[t] = __ldcg(gi + t);
   }
+  // this lane's part of the warp's 8 rows, in accumulator layout (row g, columns 8b + 2q, +1)
+  const int row = r0 + 8 * warp + g;
+  const bool row_ok = row < a.N;
+  double acc[16][2];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    double2 v = make_double2(0.0, 0.0);
+    if (row_ok) v = __ldcg(reinterpret_cast<const double2*>(Ain + (size_t)(8 * warp + g) * a.ld + 8 * b + 2 * q));
+    acc[b][0] = v.x;
+    acc[b][1] = v.y;
+  }
+  const long long c_acc = ph ? clock64() : 0;
   cp_async_wait<0>();
   csync();
-  for (int c0 = 0; c0 < nb; c0 += SB) {
-    panel_solve32(T + c0, nr, S + c0 * SP + c0, dsm + c0, binv + (c0 / SB) * INV_SUB, warp, lane, DF_CONSUMERS);
-    csync();
-    const int base = c0 + SB, rem = nb - base;
-    if (rem > 0) {
-      smem_update<false>(T + base, T + c0, S + base * SP + c0, dsm + c0, nr, rem, SB, warp, lane, DF_CONSUMERS);
-      csync();
+  const long long c_loaded = ph ? clock64() : 0;
+
+  const int src0 = (lane & ~3) | (q >> 1), src1 = src0 + 2, odd = q & 1;
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    // X_b = R_b Binv_b^T
+    const double r_0 = quad_afrag(acc[b], src0, odd, 0), r_1 = quad_afrag(acc[b], src1, odd, 0);
+    const double i_0 = binv[b * INV_BLK + g * IP + q], i_1 = binv[b * INV_BLK + g * IP + 4 + q];
+    double x[2] = {0.0, 0.0};
+    dmma884(x, r_0, i_0);
+    dmma884(x, r_1, i_1);
+    acc[b][0] = x[0];
+    acc[b][1] = x[1];
+    if (b < 15) {
+      // A fragments of -(X_b D_b), then the independent updates of every later block
+      const double a_0 = -(quad_afrag(x, src0, odd, 0) * dsm[8 * b + q]);
+      const double a_1 = -(quad_afrag(x, src1, odd, 0) * dsm[8 * b + 4 + q]);
+      const double* Sb = S + g * SP + 8 * b + q;
+#pragma unroll
+      for (int b2 = b + 1; b2 < 16; ++b2) {
+        const double f_0 = Sb[(8 * b2) * SP], f_1 = Sb[(8 * b2) * SP + 4];
+        dmma884(acc[b2], a_0, f_0);
+        dmma884(acc[b2], a_1, f_1);
+      }
     }
   }
-  double* Wout = a.W + (size_t)r0 * a.ld + k0;
-  for (int r = warp; r < nr; r += DF_CONSUMERS)
-    for (int c = lane * 2; c < nb; c += 64) {
-      const double l0 = T[r * SP + c], l1 = T[r * SP + c + 1];
-      *reinterpret_cast<double2*>(Aout + (size_t)r * a.ld + c) = make_double2(l0, l1);
-      *reinterpret_cast<double2*>(Wout + (size_t)r * a.ld + c) = make_double2(l0 * dsm[c], l1 * dsm[c + 1]);
+  const long long c_solved = ph ? clock64() : 0;
+  if (ph && tid == 0) {
+    ph[0] = c_issued - c_begin;   // L_kk cp.async issue loop
+    ph[1] = c_acc - c_issued;     // accumulator loads issued/landed
+    ph[2] = c_loaded - c_acc;     // wait for L_kk + barrier
+    ph[3] = c_solved - c_loaded;  // solve
+  }
+  if (row_ok) {
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const int c = 8 * b + 2 * q;
+      *reinterpret_cast<double2*>(Aout + (size_t)(8 * warp + g) * a.ld + c) = make_double2(acc[b][0], acc[b][1]);
+      *reinterpret_cast<double2*>(Wout + (size_t)(8 * warp + g) * a.ld + c) =
+          make_double2(acc[b][0] * dsm[c], acc[b][1] * dsm[c + 1]);
     }
+  }
 }
 
 
@@ -229,6 +293,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
   int4* ptask = tq + 2;                                 // 2 producer-side broadcast slots
   int* tq_ticket = reinterpret_cast<int*>(ptask + 2);   // ticket numbers of the published tasks
   int* ptask_ticket = tq_ticket + 2;
+  volatile int* prog0 = ptask_ticket + 2;  // k-slices consumed so far by consumer group 0
+  int* upd_done = ptask_ticket + 3;        // [2] consumer warps that finished the UPD task in queue slot 0 / 1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
@@ -239,13 +305,16 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(tq_full + s, 1);
       mbar_init(tq_empty + s, DF_CONSUMERS);
+      upd_done[s] = 0;
     }
+    *prog0 = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
   if (warp >= DF_CONSUMERS) {
     // ======================= producers =======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(DF_PRODUCER_REGS));
     const int pl = tid - DF_CTHREADS;
     const int pwarp = warp - DF_CONSUMERS;
     unsigned it = 0, pq = 0;
@@ -315,8 +384,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
   }
 
   // ======================= consumers =======================
-  const int wm = warp & 3, wn = warp >> 2;
+  // the registers the producers gave back: 232 per consumer thread -- the 64 x 32 DMMA accumulator
+  // tile (128 registers) and the one-warp 32 x 32 LDL^T of the DIAG task (row in registers) both fit
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(DF_CONSUMER_REGS));
+  const int wm = warp & 1, wn = warp >> 1;
   const int g = lane >> 2, q = lane & 3;
+  // The two halves of the consumer tile (warps 0-3: columns 0..63, warps 4-7: columns 64..127) run
+  // DF_LAG k-slices apart, and every SM sub-partition hosts one warp of each half.  One warp alone can
+  // keep its sub-partition's DMMA pipe full, so while one half loads its C tile, waits on a stage or
+  // stores its result, the other half's warp has the pipe: tile transitions cost no tensor time.
+  // There is therefore no CTA-wide barrier on the UPD path (completion is counted per warp).
+  const int grp = warp >> 2;
   unsigned it = 0, cq = 0;
   for (;;) {
     const int slot = cq & 1;
@@ -334,15 +412,18 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
       const int KT = (k1 - k0) * (DF_TILE / BK);
       const bool diag = i == j;
       const int row0 = i * DF_TILE, col0 = j * DF_TILE;
-      const int wrow = row0 + wm * 32, wcol = col0 + wn * 32;
-      const bool live = !diag || wn <= wm;  // warp tiles strictly above the diagonal are skipped
+      const int wrow = row0 + wm * 64, wcol = col0 + wn * 32;
+      const bool live = !diag || wn <= 2 * wm + 1;  // warp tiles strictly above the diagonal are skipped
       const double* Cin = k0 == 0 ? a.src : a.dst;
-      double acc[4][4][2];
+      if (grp == 1) {  // trail group 0 (the producers can always run DF_STAGES slices ahead of this group)
+        while ((int)(*prog0 - it) < DF_LAG) __nanosleep(200);
+      }
+      double acc[DF_MI][DF_NI][2];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
+      for (int mi = 0; mi < DF_MI; ++mi) {
         const int row = wrow + mi * 8 + g;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
+        for (int ni = 0; ni < DF_NI; ++ni) {
           const int col = wcol + ni * 8 + 2 * q;
           double2 cv = make_double2(0.0, 0.0);
           if (live && row < a.N && (!diag || col <= row)) {
@@ -354,35 +435,40 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
           acc[mi][ni][1] = -cv.y;
         }
       }
+      long long c_t0 = 0, c_first = 0, c_loop = 0, c_stored = 0;
+      if (a.tlog) c_t0 = clock64();
       for (int kt = 0; kt < KT; ++kt, ++it) {
         const unsigned s = it % DF_STAGES;
         mbar_wait(full + s, (it / DF_STAGES) & 1u);
+        if (a.tlog && kt == 1) c_first = clock64();
         if (live) {
-          const double* Aw = smem + s * DF_STAGE_DOUBLES + (wm * 32 + g) * LDT + q;
+          const double* Aw = smem + s * DF_STAGE_DOUBLES + (wm * 64 + g) * LDT + q;
           const double* Bw = smem + s * DF_STAGE_DOUBLES + DF_TILE * LDT + (wn * 32 + g) * LDT + q;
 #pragma unroll
           for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[4], bf[4];
+            double af[DF_MI], bf[DF_NI];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
+            for (int mi = 0; mi < DF_MI; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4];
+            for (int ni = 0; ni < DF_NI; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4];
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            for (int mi = 0; mi < DF_MI; ++mi)
 #pragma unroll
-              for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+              for (int ni = 0; ni < DF_NI; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (tid == 0) *prog0 = (int)(it + 1);
       }
+      if (a.tlog) c_loop = clock64();
       if (live) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
+        for (int mi = 0; mi < DF_MI; ++mi) {
           const int row = wrow + mi * 8 + g;
           if (row >= a.N) continue;
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
+          for (int ni = 0; ni < DF_NI; ++ni) {
             const int col = wcol + ni * 8 + 2 * q;
             if (diag && col > row) continue;
             double* p = a.dst + (size_t)row * a.ld + col;
@@ -391,15 +477,29 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
           }
         }
       }
-      csync();
-      if (tid == 0) {
-        __threadfence();
-        st_release(a.cnt + (size_t)i * a.nt + j, k1);
+      if (a.tlog) c_stored = clock64();
+      // every thread orders its own stores, the last of the eight warps publishes the tile
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const int old = atomicAdd(upd_done + slot, 1);
+        if (old == DF_CONSUMERS - 1) {
+          upd_done[slot] = 0;
+          st_release(a.cnt + (size_t)i * a.nt + j, k1);
+          if (a.tlog) a.tlog[(size_t)tnum * 8 + 1] = gtimer();
+        }
+      }
+      if (a.tlog && tid == 0) {
+        long long* ph = a.tlog + (size_t)tnum * 8 + 4;
+        ph[0] = c_first - c_t0;          // C tile in registers + first k-slice done
+        ph[1] = c_loop - c_first;        // remaining k-slices
+        ph[2] = c_stored - c_loop;       // C stores issued
+        ph[3] = clock64() - c_stored;    // fence + completion count
       }
     } else {
       __syncthreads();  // producers have published and stopped touching the ring
-      if (type == DF_DIAG) df_diag_task(a, smem, j, tid);
-      else df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid);
+      if (type == DF_DIAG) df_diag_task(a, smem, j, tid, a.tlog ? a.tlog + (size_t)tnum * 8 + 4 : nullptr);
+      else df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid, a.tlog ? a.tlog + (size_t)tnum * 8 + 4 : nullptr);
       csync();
       if (tid == 0) {
         __threadfence();
@@ -409,9 +509,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
       __syncthreads();
     }
     if (a.tlog && tid == 0) {
-      long long* rec = a.tlog + (size_t)tnum * 4;
+      long long* rec = a.tlog + (size_t)tnum * 8;
       rec[0] = t_start;
-      rec[1] = gtimer();
+      if (type != DF_UPD) rec[1] = gtimer();
       rec[2] = smid();
       rec[3] = tk.x | ((long long)tk.w << 32);
     }
@@ -533,14 +633,14 @@ int dataflow_abort_flag(cudaStream_t st, const DataflowPlan& p, int* flag) {
 int launch_ldlt_dataflow_logged(cudaStream_t st, DataflowPlan& p, const double* src, double* dst, double* Dg,
                                 double* Ginv, long long* host_log, int cap_tasks, int* ntasks) {
   cudaError_t e = cudaSuccess;
-  if (!p.d_tlog) e = cudaMalloc(&p.d_tlog, sizeof(long long) * 4 * (size_t)p.ntasks);
+  if (!p.d_tlog) e = cudaMalloc(&p.d_tlog, sizeof(long long) * 8 * (size_t)p.ntasks);
   if (e != cudaSuccess) return (int)e;
-  cudaMemsetAsync(p.d_tlog, 0, sizeof(long long) * 4 * (size_t)p.ntasks, st);
+  cudaMemsetAsync(p.d_tlog, 0, sizeof(long long) * 8 * (size_t)p.ntasks, st);
   df_launch(st, p, src, dst, Dg, Ginv, p.d_tlog);
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return (int)e;
   const int n = p.ntasks < cap_tasks ? p.ntasks : cap_tasks;
-  e = cudaMemcpy(host_log, p.d_tlog, sizeof(long long) * 4 * (size_t)n, cudaMemcpyDeviceToHost);
+  e = cudaMemcpy(host_log, p.d_tlog, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost);
   *ntasks = n;
   return (int)e;
 }

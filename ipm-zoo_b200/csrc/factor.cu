@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(256) k_diag_ldlt(const double* src, double* ds
   double* S = sm;
   double* dsm = sm + NB * SP;
   double* dinv = dsm + NB;
-  double* colbuf = dinv + NB;          // 2 x 32
-  double* binv = colbuf + 2 * SB;      // 4 sub-blocks x 4 blocks x INV_BLK
+  double* colbuf = dinv + NB;          // exchange buffers of warp_ldlt32
+  double* binv = colbuf + CBUF;      // 4 sub-blocks x 4 blocks x INV_BLK
   const int p = active ? active[blockIdx.y] : blockIdx.y;
   const double* A = src + (size_t)p * sK + (size_t)k0 * ld + k0;
   double* O = dst + (size_t)p * sK + (size_t)k0 * ld + k0;

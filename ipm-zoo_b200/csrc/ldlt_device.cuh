@@ -15,7 +15,7 @@ constexpr int SP = 132;  // shared-memory pitch: 132 mod 16 == 4 -> DMMA fragmen
 constexpr int RB = 64;   // panel rows per CTA in k_trsm_panel
 constexpr int WLD = 256; // leading dimension of the scaled-panel buffer W = L D (two NB-wide panels)
 
-constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB + 2 * 32 + 16 * 96) * sizeof(double);
+constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB + 8 * 32 + 16 * 96) * sizeof(double);
 constexpr size_t TRSM_SMEM = (size_t)((NB + RB) * SP + NB + 16 * 96) * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -121,36 +121,72 @@ constexpr int IP = 12;               // pitch of an 8 x 8 inverse block (conflic
 constexpr int INV_BLK = 8 * IP;      // doubles per inverse block
 constexpr int INV_SUB = 4 * INV_BLK; // per 32-wide sub-block
 
-// Unpivoted LDL^T of one 32 x 32 diagonal sub-block by ONE warp: lane r keeps row r in
-// registers; the finished column c is exchanged through a double-buffered shared-memory line
-// (one store + broadcast loads; shuffles cost ~8 issue cycles per value on this part).  The
-// dependent chain per pivot is FMA -> STS -> LDS -> reciprocal -> MUL.  Then the 8 x 8 blocks
+// Unpivoted LDL^T of one 32 x 32 diagonal sub-block by ONE warp: lane r keeps row r in registers.
+// Columns are eliminated FOUR at a time: the lanes exchange their four current column entries
+// through shared memory (one store, broadcast loads), every lane factors the 4 x 4 diagonal block
+// redundantly (the dependent chain of the pivots: 4 reciprocals), solves its own row against it
+// and, after one more exchange of the unscaled entries w = l d, applies the rank-4 update to its
+// row.  One exchange round trip per 4 pivots instead of per pivot.  Then the 8 x 8 blocks
 // Binv_b = D_b^-1 L_bb^-1 (b = 0..3) are formed so that the rows below are solved on the tensor
 // pipe:  X_b = R_b Binv_b^T  with  R_b = A_b - sum_{l<b} X_l D_l L_bl^T.
+constexpr int CBUF = 8 * SB;  // two 32 x 4 exchange buffers
+__device__ __forceinline__ double pivot_of(double d) { return d == 0.0 ? 1e-8 : d; }  // LinearSolvers.cpp:28
 __device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* dsm, double* dinv, double* colbuf,
                                             double* binv, int lane) {
   double a[SB];
 #pragma unroll
   for (int c = 0; c < SB; ++c) a[c] = (lane < jb && c <= lane) ? S[(j0 + lane) * SP + j0 + c] : 0.0;
+  double* xbuf = colbuf;            // [32][4] current entries of the four columns
+  double* wbuf = colbuf + 4 * SB;   // [32][4] the same after elimination inside the block (w = l d)
 #pragma unroll
-  for (int c = 0; c < SB; ++c) {
-    if (c < jb) {
-      double* buf = colbuf + (c & 1) * SB;
-      buf[lane] = a[c];
+  for (int cb = 0; cb < SB / 4; ++cb) {
+    constexpr int dummy = 0; (void)dummy;
+    const int c0 = 4 * cb;
+    if (c0 < jb) {
+      *reinterpret_cast<double2*>(xbuf + 4 * lane) = make_double2(a[c0], a[c0 + 1]);
+      *reinterpret_cast<double2*>(xbuf + 4 * lane + 2) = make_double2(a[c0 + 2], a[c0 + 3]);
       __syncwarp();
-      double col[SB];
+      // 4 x 4 diagonal block (rows c0..c0+3), lower part, unscaled
+      const double p00 = xbuf[4 * c0];
+      const double2 p1 = *reinterpret_cast<const double2*>(xbuf + 4 * (c0 + 1));      // p10 p11
+      const double2 p2a = *reinterpret_cast<const double2*>(xbuf + 4 * (c0 + 2));     // p20 p21
+      const double p22 = xbuf[4 * (c0 + 2) + 2];
+      const double2 p3a = *reinterpret_cast<const double2*>(xbuf + 4 * (c0 + 3));     // p30 p31
+      const double2 p3b = *reinterpret_cast<const double2*>(xbuf + 4 * (c0 + 3) + 2); // p32 p33
+      const double d0 = pivot_of(p00), r0 = fast_rcp(d0);
+      const double l10 = p1.x * r0, l20 = p2a.x * r0, l30 = p3a.x * r0;
+      const double d1 = pivot_of(fma(-l10, p1.x, p1.y)), r1 = fast_rcp(d1);
+      const double t21 = fma(-l20, p1.x, p2a.y), t31 = fma(-l30, p1.x, p3a.y);
+      const double l21 = t21 * r1, l31 = t31 * r1;
+      const double d2 = pivot_of(fma(-l21, t21, fma(-l20, p2a.x, p22))), r2 = fast_rcp(d2);
+      const double t32 = fma(-l31, t21, fma(-l30, p2a.x, p3b.x));
+      const double l32 = t32 * r2;
+      const double d3 = pivot_of(fma(-l32, t32, fma(-l31, t31, fma(-l30, p3a.x, p3b.y)))), r3 = fast_rcp(d3);
+      // this lane's row against the block: l_k = w_k / d_k, w_k = x_k - sum_{m<k} l_m (w of row c0+k)_m
+      const double w0 = a[c0], li0 = w0 * r0;
+      const double w1 = fma(-li0, p1.x, a[c0 + 1]), li1 = w1 * r1;
+      const double w2 = fma(-li1, t21, fma(-li0, p2a.x, a[c0 + 2])), li2 = w2 * r2;
+      const double w3 = fma(-li2, t32, fma(-li1, t31, fma(-li0, p3a.x, a[c0 + 3]))), li3 = w3 * r3;
+      *reinterpret_cast<double2*>(wbuf + 4 * lane) = make_double2(w0, w1);
+      *reinterpret_cast<double2*>(wbuf + 4 * lane + 2) = make_double2(w2, w3);
+      if (lane == c0) {
+        *reinterpret_cast<double2*>(dsm + j0 + c0) = make_double2(d0, d1);
+        *reinterpret_cast<double2*>(dsm + j0 + c0 + 2) = make_double2(d2, d3);
+        *reinterpret_cast<double2*>(dinv + j0 + c0) = make_double2(r0, r1);
+        *reinterpret_cast<double2*>(dinv + j0 + c0 + 2) = make_double2(r2, r3);
+      }
+      if (lane > c0) a[c0] = li0;
+      if (lane > c0 + 1) a[c0 + 1] = li1;
+      if (lane > c0 + 2) a[c0 + 2] = li2;
+      if (lane > c0 + 3) a[c0 + 3] = li3;
+      __syncwarp();
+      // rank-4 update of this lane's row: a[j] -= sum_k l_k w_jk  (the next block's columns first)
 #pragma unroll
-      for (int c2 = 0; c2 < SB; ++c2)
-        if (c2 >= c) col[c2] = buf[c2];
-      double d = col[c];
-      if (d == 0.0) d = 1e-8;  // LinearSolvers.cpp:28
-      const double rinv = fast_rcp(d);
-      const double l = a[c] * rinv;
-#pragma unroll
-      for (int c2 = 0; c2 < SB; ++c2)
-        if (c2 > c) a[c2] -= l * col[c2];
-      if (lane == c) { dsm[j0 + c] = d; dinv[j0 + c] = rinv; }
-      if (lane > c) a[c] = l;
+      for (int j = c0 + 4; j < SB; ++j) {
+        const double2 wa = *reinterpret_cast<const double2*>(wbuf + 4 * j);
+        const double2 wb = *reinterpret_cast<const double2*>(wbuf + 4 * j + 2);
+        a[j] = fma(-li3, wb.y, fma(-li2, wb.x, fma(-li1, wa.y, fma(-li0, wa.x, a[j]))));
+      }
     }
   }
 #pragma unroll

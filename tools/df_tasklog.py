@@ -15,7 +15,7 @@ L = z.lib()
 nt = L.ipmz_debug_factor_ntasks(f._h)
 if nt == 0:
     print("dataflow plan not active"); sys.exit(0)
-log = np.zeros((nt, 4), dtype=np.int64); got = C.c_int(); sim = C.c_double()
+log = np.zeros((nt, 8), dtype=np.int64); got = C.c_int(); sim = C.c_double()
 rc = L.ipmz_debug_factor_tasklog(f._h, log.ctypes.data_as(C.POINTER(C.c_longlong)), nt, C.byref(got), C.byref(sim))
 print("tasklog rc", rc, "tasks", got.value, "simulated makespan us", sim.value)
 t0 = log[:, 0].min(); st = (log[:, 0] - t0) * 1e-3; en = (log[:, 1] - t0) * 1e-3
@@ -27,6 +27,20 @@ for t, name in ((0, "DIAG"), (1, "TRSM"), (2, "UPD")):
     if m.any():
         print("%s: n=%d mean %.2f us  p10 %.2f p50 %.2f p90 %.2f max %.2f  total %.1f ms-SM" % (
             name, m.sum(), dur[m].mean(), *np.percentile(dur[m], [10, 50, 90]), dur[m].max(), dur[m].sum() * 1e-3))
+dm = typ == 0
+print("DIAG phases (cycles, median): load %d | 4 x ldlt32 %d | elimination loop %d | store %d" % tuple(
+    np.median(log[dm, 4 + i]) for i in range(4)))
+tm = typ == 1
+print("TRSM phases (cycles, median): L_kk issue %d | acc loads %d | wait+barrier %d | solve %d | (task total %d)" % (
+    *(np.median(log[tm, 4 + i]) for i in range(4)), np.median(dur[tm]) * 1965))
+um = typ == 2
+for kk in (1, 8):
+    mk = um & (K == kk)
+    if mk.any():
+        print("UPD K=%d phases (cycles, median): C tile + first slice %d | other slices %d (%.0f per slice) | store issue %d | barrier+fence+release %d | task total %d" % (
+            kk, *(np.median(log[mk, 4 + i]) for i in range(2)), np.median(log[mk, 5]) / (8 * kk - 1),
+            *(np.median(log[mk, 4 + i]) for i in (2, 3)), np.median(dur[mk]) * 1965))
+# time from the end of the previous task on the SM to the start of this one (task switch)
 m = typ == 2
 for k in range(1, 9):
     mk = m & (K == k)
