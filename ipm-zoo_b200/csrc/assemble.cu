@@ -11,53 +11,81 @@
 
 namespace ipmz {
 
-__global__ void __launch_bounds__(256) k_assemble(View v) {
+// One warp per row of K, 8 rows per CTA, 16-byte accesses (every leading dimension is a multiple
+// of 4 doubles and every row base 32-byte aligned; the padding of Q / M / MT is zero).
+constexpr int AS_ROWS = 8;
+
+__device__ __forceinline__ void copy_row2(double* __restrict__ dst, const double* __restrict__ src, int len2, int lane) {
+  for (int c = lane; c < len2; c += 32)
+    reinterpret_cast<double2*>(dst)[c] = reinterpret_cast<const double2*>(src)[c];
+}
+
+__global__ void __launch_bounds__(32 * AS_ROWS) k_assemble(View v) {
   const int p = problem_of(v);
   const Shape& s = v.s;
-  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * AS_ROWS + (threadIdx.x >> 5);
+  if (r >= v.N) return;
   double* V = v.V + (size_t)p * v.sp;
   double* Krow = v.K + (size_t)p * v.sK + (size_t)r * v.ldk;
+  const bool even_n = (s.n & 1) == 0;  // the (1,2) / (2,2) blocks start at column n: 16-byte aligned only then
   if (r < s.n) {
-    double diag = 0.0;
     const double* q = v.Q + (size_t)p * v.sQ + (size_t)r * v.ldq;
-    double dii = q[r];
-    if (s.ylo) dii = dii + inv_guard(nslot(V, s, YS)[r]) * nslot(V, s, LAMY)[r];
-    if (s.zup) dii = dii + inv_guard(nslot(V, s, ZS)[r]) * nslot(V, s, LAMZ)[r];
-    diag = dii;
-    for (int c = threadIdx.x; c < s.n; c += blockDim.x) Krow[c] = (c == r) ? diag : q[c];
+    copy_row2(Krow, q, (v.normal ? v.ldk : s.n) >> 1, lane);  // normal: N = n and ldk = ldq = pad4(n), padding copies zeros
+    if (!v.normal && (s.n & 1)) { if (lane == 0) Krow[s.n - 1] = q[s.n - 1]; }
+    __syncwarp();
+    if (lane == 0) {
+      double dii = q[r];
+      if (s.ylo) dii = dii + inv_guard(nslot(V, s, YS)[r]) * nslot(V, s, LAMY)[r];
+      if (s.zup) dii = dii + inv_guard(nslot(V, s, ZS)[r]) * nslot(V, s, LAMZ)[r];
+      Krow[r] = dii;
+    }
     if (!v.normal) {
       const double* mt = v.MT + (size_t)p * v.sMT + (size_t)r * v.ldmt;
-      for (int c = threadIdx.x; c < s.m; c += blockDim.x) Krow[s.n + c] = mt[c];
+      if (even_n) copy_row2(Krow + s.n, mt, (s.m + 1) >> 1, lane);  // odd m: also copies one zero of MT's padding into K's
+      else for (int c = lane; c < s.m; c += 32) Krow[s.n + c] = mt[c];
+      for (int c = v.N + lane; c < v.ldk; c += 32) Krow[c] = 0.0;
     }
   } else {
     const int j = r - s.n;
     const double* mr = v.M + (size_t)p * v.sM + (size_t)j * v.ldm;
-    for (int c = threadIdx.x; c < s.n; c += blockDim.x) Krow[c] = mr[c];
+    copy_row2(Krow, mr, s.n >> 1, lane);
+    if (s.n & 1) { if (lane == 0) Krow[s.n - 1] = mr[s.n - 1]; }
     const double wi = v.winv[(size_t)p * s.ms + j];
-    for (int c = threadIdx.x; c < s.m; c += blockDim.x) Krow[s.n + c] = (c == j) ? -wi : 0.0;
+    for (int c = lane; c < s.m; c += 32) Krow[s.n + c] = (c == j) ? -wi : 0.0;
+    for (int c = v.N + lane; c < v.ldk; c += 32) Krow[c] = 0.0;
   }
-  for (int c = v.N + threadIdx.x; c < v.ldk; c += blockDim.x) Krow[c] = 0.0;
 }
 
-__global__ void __launch_bounds__(256) k_scale_cols(const double* __restrict__ in, double* __restrict__ out, int ld,
-                                                    size_t sM, int cols, const double* __restrict__ d, size_t sd,
-                                                    const int* __restrict__ active) {
+__global__ void __launch_bounds__(32 * AS_ROWS) k_scale_cols(const double* __restrict__ in, double* __restrict__ out,
+                                                             int ld, size_t sM, int rows, int cols,
+                                                             const double* __restrict__ d, size_t sd,
+                                                             const int* __restrict__ active) {
   const int p = active ? active[blockIdx.y] : blockIdx.y;
-  const double* src = in + (size_t)p * sM + (size_t)blockIdx.x * ld;
-  double* dst = out + (size_t)p * sM + (size_t)blockIdx.x * ld;
-  const double* dv = d + (size_t)p * sd;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) dst[c] = src[c] * dv[c];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * AS_ROWS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const double2* src = reinterpret_cast<const double2*>(in + (size_t)p * sM + (size_t)r * ld);
+  double2* dst = reinterpret_cast<double2*>(out + (size_t)p * sM + (size_t)r * ld);
+  const double2* dv = reinterpret_cast<const double2*>(d + (size_t)p * sd);
+  // ld and the stride of d are multiples of 4 and the padding of `in` is zero: whole double2's
+  for (int c = lane; c < (cols + 1) >> 1; c += 32) {
+    const double2 a = src[c], w = dv[c];
+    dst[c] = make_double2(a.x * w.x, 2 * c + 1 < cols ? a.y * w.y : 0.0);
+  }
 }
 
 void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
                        size_t sM, int rows, int cols, const double* d, size_t sd) {
   if (rows <= 0 || cols <= 0 || nslots <= 0) return;
-  k_scale_cols<<<dim3(rows, nslots), 256, 0, st>>>(in, out, ld, sM, cols, d, sd, active); count_launch();
+  k_scale_cols<<<dim3((rows + AS_ROWS - 1) / AS_ROWS, nslots), 32 * AS_ROWS, 0, st>>>(in, out, ld, sM, rows, cols, d, sd,
+                                                                                     active);
+  count_launch();
 }
 
 void launch_assemble(cudaStream_t st, const View& v, int nslots) {
-  dim3 grid(v.N, nslots);
-  k_assemble<<<grid, 256, 0, st>>>(v); count_launch();
+  dim3 grid((v.N + AS_ROWS - 1) / AS_ROWS, nslots);
+  k_assemble<<<grid, 32 * AS_ROWS, 0, st>>>(v); count_launch();
 }
 
 }  // namespace ipmz

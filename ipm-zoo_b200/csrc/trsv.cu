@@ -176,6 +176,104 @@ __global__ void __launch_bounds__(256) k_trsv_backward(TrsvArgs a) {
 
 
 // ------------------------------------------------------------------------------------------
+// Small systems (N <= TRSV_SMALL_MAX; the batched QPs of cfg4): ONE CTA per problem runs the
+// forward sweep, the pivot scaling and the backward sweep back to back with x in shared memory --
+// no inter-CTA flags, one launch per solve, and the factor is read a second time while it is still
+// in L2.  Block rows of 64: the part left of (below) the diagonal block is a coalesced
+// matrix-vector product over the whole CTA, the 64 x 64 diagonal block is solved by one warp.
+constexpr int TRSV_SMALL_MAX = 512;
+
+__global__ void __launch_bounds__(256, 4) k_trsv_small(TrsvArgs a) {
+  extern __shared__ double sx[];  // x, padded to a multiple of 64
+  __shared__ double Ld[TB * TP];
+  __shared__ double part[4][TB];
+  const int slot = blockIdx.x;
+  const int p = a.active ? a.active[slot] : slot;
+  const double* K = a.K + (size_t)p * a.sK;
+  const double* Dg = a.Dg + (size_t)p * a.sD;
+  double* x = a.x + (size_t)p * a.sx;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = a.nblk, N = a.N;
+  for (int i = tid; i < nblk * TB; i += 256) sx[i] = i < N ? x[i] : 0.0;
+  __syncthreads();
+
+  // ---- forward: L y = b ----
+  for (int r = 0; r < nblk; ++r) {
+    const int R0 = r * TB, nr = min(TB, N - R0);
+    for (int idx = tid; idx < TB * TB; idx += 256) {
+      const int i = idx / TB, c = idx - i * TB;
+      Ld[i * TP + c] = (i < nr && c < i) ? K[(size_t)(R0 + i) * a.ld + R0 + c] : 0.0;
+    }
+    // rows 8*warp .. +7 of the block: dot products with the finished part of y
+    double s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0;
+    for (int c0 = 0; c0 < R0; c0 += 32) {
+      const double xc = sx[c0 + lane];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 8 * warp + i;
+        if (row < nr) s[i] = fma(K[(size_t)(R0 + row) * a.ld + c0 + lane], xc, s[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double v = s[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sx[R0 + 8 * warp + i] -= v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double y0 = sx[R0 + lane], y1 = sx[R0 + lane + 32];
+#pragma unroll 8
+      for (int c = 0; c < TB; ++c) {
+        const double yc = __shfl_sync(0xffffffffu, c < 32 ? y0 : y1, c & 31);
+        if (lane > c) y0 -= Ld[lane * TP + c] * yc;
+        if (lane + 32 > c) y1 -= Ld[(lane + 32) * TP + c] * yc;
+      }
+      sx[R0 + lane] = y0;
+      sx[R0 + lane + 32] = y1;
+    }
+    __syncthreads();
+  }
+  // ---- pivots ----
+  for (int i = tid; i < N; i += 256) sx[i] = sx[i] / Dg[i];
+  __syncthreads();
+  // ---- backward: L^T x = y ----
+  const int c = tid & 63, grp = tid >> 6;
+  for (int r = nblk - 1; r >= 0; --r) {
+    const int R0 = r * TB, nr = min(TB, N - R0);
+    for (int idx = tid; idx < TB * TB; idx += 256) {
+      const int i = idx / TB, cc = idx - i * TB;
+      Ld[i * TP + cc] = (i < nr && cc < i) ? K[(size_t)(R0 + i) * a.ld + R0 + cc] : 0.0;
+    }
+    // column R0 + c against the finished rows below the block, rows split over the 4 thread groups
+    double sacc = 0.0;
+    if (c < nr) {
+      for (int row = R0 + TB + grp; row < N; row += 4) sacc = fma(K[(size_t)row * a.ld + R0 + c], sx[row], sacc);
+    }
+    part[grp][c] = sacc;
+    __syncthreads();
+    if (tid < TB) sx[R0 + tid] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = sx[R0 + lane], x1 = sx[R0 + lane + 32];
+#pragma unroll 8
+      for (int i = TB - 1; i >= 0; --i) {
+        const double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
+        if (lane < i) x0 -= Ld[i * TP + lane] * xi;
+        if (lane + 32 < i) x1 -= Ld[i * TP + lane + 32] * xi;
+      }
+      sx[R0 + lane] = x0;
+      sx[R0 + lane + 32] = x1;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += 256) x[i] = sx[i];
+}
+
+// ------------------------------------------------------------------------------------------
 // Streaming solves for one large factor (single matrix, N >= the dataflow threshold):
 //   forward   y_r = L_rr^-1   (b_r       - sum_{j<r} L_rj   y_j)
 //   backward  x_r = L_rr^-T   (y_r / D_r - sum_{j>r} L_jr^T x_j)
@@ -633,6 +731,13 @@ void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, c
     return;
   }
   const int nblk = (fp.N + TB - 1) / TB;
+  if (fp.N <= TRSV_SMALL_MAX) {
+    TrsvArgs a{};
+    a.K = K; a.Dg = Dg; a.x = x; a.ld = fp.ld; a.N = fp.N; a.nblk = nblk;
+    a.sK = fp.sK; a.sD = fp.sD; a.sx = sx; a.active = fp.active;
+    k_trsv_small<<<fp.nslots, 256, sizeof(double) * (size_t)nblk * TB, st>>>(a); count_launch();
+    return;
+  }
   TrsvArgs a;
   a.K = K; a.Dg = Dg; a.x = x; a.ld = fp.ld; a.N = fp.N; a.nblk = nblk;
   a.sK = fp.sK; a.sD = fp.sD; a.sx = sx;
