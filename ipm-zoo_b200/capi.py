@@ -53,7 +53,8 @@ class _Result(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libipmz_b200.so")
+    # IPMZ_LIB: A/B runs of two builds inside one GPU call (tools/); the product is the in-tree library
+    return os.environ.get("IPMZ_LIB") or os.path.join(HERE, "libipmz_b200.so")
 
 
 def build(verbose=False):
