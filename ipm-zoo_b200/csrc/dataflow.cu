@@ -57,6 +57,7 @@ struct DfArgs {
   const int4* tasks;
   int* ticket;
   int* abort;
+  int* sticky;  // never reset: set together with abort, read by the host after a solve
   int* rdy;
   int* cnt;
   long long* tlog;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void wait_deps(const DfArgs& a, const int4 tk, int la
       if (t0 == 0) t0 = gtimer();
       const bool bail = ld_acquire(a.abort) != 0 || gtimer() - t0 > 4000000000LL;
       if (__any_sync(0xffffffffu, bail)) {
-        if (lane == 0) atomicExch(a.abort, 1);
+        if (lane == 0) { atomicExch(a.abort, 1); atomicExch(a.sticky, 1); }
         break;
       }
     }
@@ -578,8 +579,8 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   if (e == cudaSuccess) e = cudaMemset(p->W, 0, sizeof(double) * (size_t)N * ld);
   if (e == cudaSuccess) e = cudaMalloc(&p->xl, sizeof(double) * 2 * (size_t)s.nt * NB);
   if (e == cudaSuccess) e = cudaMemset(p->xl, 0xff, sizeof(double) * 2 * (size_t)s.nt * NB);  // = the "not yet" pattern
-  if (e == cudaSuccess) e = cudaMalloc(&p->solve_ticket, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(p->solve_ticket, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&p->solve_ticket, 2 * sizeof(int));  // [0] solve ticket, [1] sticky abort flag
+  if (e == cudaSuccess) e = cudaMemset(p->solve_ticket, 0, 2 * sizeof(int));
   if (e == cudaSuccess) {
     static_assert(sizeof(DfTask) == sizeof(int4), "DfTask is uploaded as int4");
     e = cudaMemcpy(p->d_tasks, s.tasks.data(), sizeof(int4) * s.tasks.size(), cudaMemcpyHostToDevice);
@@ -609,7 +610,7 @@ static void df_launch(cudaStream_t st, const DataflowPlan& p, const double* src,
   cudaMemsetAsync(p.d_flags, 0, sizeof(int) * p.flag_ints, st);
   DfArgs a;
   a.src = src; a.dst = dst; a.W = p.W; a.Dg = Dg; a.Ginv = Ginv; a.tasks = p.d_tasks;
-  a.ticket = p.d_flags; a.abort = p.d_flags + 1; a.rdy = p.d_flags + 2; a.cnt = a.rdy + (size_t)p.nt * p.nt;
+  a.ticket = p.d_flags; a.abort = p.d_flags + 1; a.sticky = p.solve_ticket + 1; a.rdy = p.d_flags + 2; a.cnt = a.rdy + (size_t)p.nt * p.nt;
   a.tlog = tlog;
   a.N = p.N; a.ld = p.ld; a.nt = p.nt; a.ntasks = p.ntasks;
   const int ctas = p.nsm < p.ntasks ? p.nsm : p.ntasks;
@@ -622,9 +623,10 @@ void launch_ldlt_dataflow(cudaStream_t st, const DataflowPlan& p, const double* 
   df_launch(st, p, src, dst, Dg, Ginv, nullptr);
 }
 
-// 0 = ok, 1 = a dependency wait hit the watchdog (results invalid)
+// 0 = ok, 1 = a dependency wait of a factorization or a solve on this plan hit its watchdog since the
+// plan was created (results invalid; the flag is sticky)
 int dataflow_abort_flag(cudaStream_t st, const DataflowPlan& p, int* flag) {
-  cudaError_t e = cudaMemcpyAsync(flag, p.d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaMemcpyAsync(flag, p.solve_ticket + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   return (int)e;
 }

@@ -134,6 +134,11 @@ int ipmz_factor_run(ipmz_factor_handle h, int reps, int nrhs, double* ms_total) 
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->e0, h->e1));
   if (ms_total) *ms_total = ms;
+  if (h->df) {
+    int aborted = 0;
+    CUDA_TRY((cudaError_t)dataflow_abort_flag(h->st, *h->df, &aborted));
+    if (aborted) return ipmz_fail(IPMZ_ERR_CUDA, "dataflow factorization / streaming solve: a dependency wait timed out");
+  }
   return IPMZ_OK;
 }
 

@@ -337,7 +337,8 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
       launch_matvec(w.st, nslots, v.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.out, so, v.Qd, s.ns);
       if (s.m > 0) {
         launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.out + s.ns, so, v.tn, s.ns);
-        launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.out, so, v.Mx, s.ms);
+        // first refinement step: out's dx is still the vector the condensed solve just multiplied by M (v.Mx)
+        if (r > 0) launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.out, so, v.Mx, s.ms);
       }
       launch_aug_residual(w.st, v, nslots);
       condensed_solve(w, v, nslots, v.resid, 1);
@@ -413,6 +414,11 @@ static int run_ipm(Workspace& w, double* ms_out) {
   CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
   if (ms_out) *ms_out = ms;
   w.tr_iters = it;
+  if (w.df) {
+    int aborted = 0;
+    CUDA_TRY((cudaError_t)dataflow_abort_flag(w.st, *w.df, &aborted));
+    if (aborted) return fail(IPMZ_ERR_CUDA, "dataflow factorization / streaming solve: a dependency wait timed out");
+  }
   return IPMZ_OK;
 }
 

@@ -304,6 +304,7 @@ struct SvArgs {
   double* x;      // in: right-hand side, out: solution
   double* xl;     // [2][nblk*128] exchange buffers: forward blocks y_r, backward blocks x_r
   int* ticket;
+  int* sticky;    // set when a poll hits its watchdog (never reset; read by the host after a solve)
   int ld, N, nblk;
   long long* tlog;  // debug: [2][nblk][16] stamps (nullptr: off)
 };
@@ -319,7 +320,7 @@ __device__ __forceinline__ void sv_cp16(void* smem_dst, const void* gsrc, int sr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(src_bytes));
 }
 
-__device__ __forceinline__ double sv_poll(const double* p) {
+__device__ __forceinline__ double sv_poll(const double* p, int* sticky) {
   unsigned long long v;
   long long t0 = 0;
   for (unsigned spin = 0;; ++spin) {
@@ -328,7 +329,10 @@ __device__ __forceinline__ double sv_poll(const double* p) {
     if ((spin & 4095u) == 4095u) {  // watchdog: a protocol bug must not hang the device
       const long long t = sv_now();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000LL) break;
+      else if (t - t0 > 4000000000LL) {
+        if (sticky) atomicExch(sticky, 1);  // the host reports the solve as failed
+        break;
+      }
     }
   }
   return __longlong_as_double((long long)v);
@@ -339,8 +343,8 @@ __device__ __forceinline__ unsigned long long sv_peek(const double* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ double sv_poll_from(unsigned long long v, const double* p) {
-  return v != SV_NOT_YET ? __longlong_as_double((long long)v) : sv_poll(p);
+__device__ __forceinline__ double sv_poll_from(unsigned long long v, const double* p, int* sticky) {
+  return v != SV_NOT_YET ? __longlong_as_double((long long)v) : sv_poll(p, sticky);
 }
 __device__ __forceinline__ void sv_publish(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(__double_as_longlong(v)) : "memory");
@@ -486,7 +490,7 @@ __device__ __forceinline__ void sv_block_row(const SvArgs& a, const int r, doubl
   };
   auto chunk = [&](const double* x_blk, int q, unsigned long long peeked, int slot0, bool real) {
     if (FWD) {
-      const double xc = real ? sv_poll_from(peeked, chunk_src(x_blk, q)) : 0.0;
+      const double xc = real ? sv_poll_from(peeked, chunk_src(x_blk, q), a.sticky) : 0.0;
 #pragma unroll
       for (int sl = 0; sl < SV_SPT; ++sl) {
         int slot = slot0 + sl;
@@ -497,7 +501,7 @@ __device__ __forceinline__ void sv_block_row(const SvArgs& a, const int r, doubl
       }
     } else {
       double xm = 0.0;
-      if (real && (lane >> 2) == q) xm = sv_poll_from(peeked, chunk_src(x_blk, q));
+      if (real && (lane >> 2) == q) xm = sv_poll_from(peeked, chunk_src(x_blk, q), a.sticky);
       __syncwarp();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -535,7 +539,7 @@ __device__ __forceinline__ void sv_block_row(const SvArgs& a, const int r, doubl
         const int row = SV_SR * (e >> 1) + 2 * warp + (e & 1);
         if (row < nr) rhs_val = a.x[R0 + row];
       } else if (tid < nr) {
-        rhs_val = sv_poll(fwd + R0 + tid) / a.Dg[R0 + tid];
+        rhs_val = sv_poll(fwd + R0 + tid, a.sticky) / a.Dg[R0 + tid];
       }
     }
     if (real) {
@@ -546,9 +550,9 @@ __device__ __forceinline__ void sv_block_row(const SvArgs& a, const int r, doubl
         double xq[4];
         if (FWD) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xq[q] = sv_poll(x_blk + 32 * q + lane);
+          for (int q = 0; q < 4; ++q) xq[q] = sv_poll(x_blk + 32 * q + lane, a.sticky);
         } else {
-          xq[0] = lane < 16 ? sv_poll(x_blk + 16 * (lane >> 1) + 2 * warp + (lane & 1)) : 0.0;
+          xq[0] = lane < 16 ? sv_poll(x_blk + 16 * (lane >> 1) + 2 * warp + (lane & 1), a.sticky) : 0.0;
         }
 #pragma unroll
         for (int sl = 0; sl < SV_SPT; ++sl) {
@@ -724,7 +728,7 @@ void launch_ldlt_solve(cudaStream_t st, const FactorPlan& fp, const double* K, c
   if (use_stream && fp.df && fp.nslots == 1 && !fp.active) {
     const DataflowPlan& p = *fp.df;
     SvArgs v;
-    v.K = K; v.Dg = Dg; v.Ginv = fp.inv; v.x = x; v.xl = p.xl; v.ticket = p.solve_ticket;
+    v.K = K; v.Dg = Dg; v.Ginv = fp.inv; v.x = x; v.xl = p.xl; v.ticket = p.solve_ticket; v.sticky = p.solve_ticket + 1;
     v.ld = fp.ld; v.N = fp.N; v.nblk = p.nt; v.tlog = g_sv_log;
     cudaMemsetAsync(p.xl, 0xff, sizeof(double) * 2 * (size_t)p.nt * SV_TB, st);  // every entry "not yet"
     k_trsv_fused<<<2 * p.nt, SV_THREADS, SV_SMEM, st>>>(v); count_launch();

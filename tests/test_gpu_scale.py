@@ -177,3 +177,55 @@ print("ok", r1, r2)
     env = dict(os.environ, IPMZ_DATAFLOW_MIN_N="128", PYTHONPATH=root)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cfg5_portfolio_full_size_vs_golden(z):
+    """cfg5 at BASELINE.json's size (n = 4096, N = 4097 augmented: a one-row ragged tile in the
+    dataflow factorization and the streaming solves) against the oracle trace committed by
+    tests/golden/make_golden_cfg5.py: same iteration count, objective within 1e-8, same x."""
+    g = np.load(os.path.join(GOLD, "cfg5_portfolio_4096.npz"))
+    p = P.portfolio(4096, 32, 1e-6, 5)
+    k = int(g["iterations"])
+    for red in (z.AUGMENTED, z.NORMAL):
+        s = z.Solver(z.Problem.from_data(p), z.Options(reduction=red))
+        r = s.solve()
+        tr = s.trace(r.iterations)
+        x = s.iterate()[:p.n]
+        s.close()
+        assert r.converged and bool(g["converged"])
+        assert r.iterations == k
+        assert abs(r.f - g["f"][k]) <= 1e-8 * max(1.0, abs(g["f"][k]))
+        f_dev = np.asarray(tr["f"][:k + 1])
+        assert np.max(np.abs(f_dev - g["f"]) / np.maximum(1.0, np.abs(g["f"]))) < 1e-8
+        assert np.max(np.abs(x - g["x"])) < 1e-7
+        assert abs(x.sum() - 1.0) < 1e-7 and x.min() > -1e-9
+
+
+@pytest.mark.parametrize("n", [1000, 3001])
+def test_dataflow_factor_is_bitwise_reproducible(n):
+    """The dataflow kernel hands tiles to whichever CTA is free, but every tile receives its updates
+    in the fixed order and K-grouping of the task list: repeated runs must agree bit for bit (a race
+    on a dependency flag or a tile would show up as run-to-run differences)."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, ipm_zoo_b200 as z
+n = %d
+rng = np.random.default_rng(3)
+S = rng.standard_normal((n, n)) / np.sqrt(n)
+A = 2.5 * np.eye(n) + 0.5 * (S + S.T)
+f = z.Factor(n); assert f.info()["dataflow"]
+f.set_matrix(A); f.set_rhs(rng.standard_normal(n))
+ref = None
+for rep in range(12):
+    f.run(1, 2)
+    L, D = f.ld(); x = f.solution()
+    cur = (L.tobytes(), D.tobytes(), x.tobytes())
+    if ref is None: ref = cur
+    assert cur == ref, "run %%d differs" %% rep
+print("ok")
+''' % n
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IPMZ_DATAFLOW_MIN_N="128", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
