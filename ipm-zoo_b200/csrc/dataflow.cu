@@ -131,7 +131,8 @@ __device__ __forceinline__ void wait_deps(const DfArgs& a, const int4 tk, int la
 }
 
 // ---- DIAG(k): LDL^T of the diagonal tile, 16 consumer warps (body of k_diag_ldlt, factor.cu) ----
-__device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k, int tid, long long* ph) {
+// preloaded: the updated tile is already in S (fused DIAGU task: written from the accumulators)
+__device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k, int tid, long long* ph, bool preloaded) {
   double* S = sm;
   double* dsm = sm + NB * SP + RB * SP;
   double* dinv = dsm + NB;
@@ -145,14 +146,16 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
 
   const long long c_begin = ph ? clock64() : 0;
   long long c_ldlt = 0;
-  if (nb < NB) {  // ragged tile: partial sub-blocks must not read uninitialised shared memory
-    for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
+  if (!preloaded) {
+    if (nb < NB) {  // ragged tile: partial sub-blocks must not read uninitialised shared memory
+      for (int i = tid; i < NB * SP; i += DF_CTHREADS) S[i] = 0.0;
+      csync();
+    }
+    async_block_load<true, DF_CTHREADS>(S, A, a.ld, nb, nb, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
     csync();
   }
-  async_block_load<true, DF_CTHREADS>(S, A, a.ld, nb, nb, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  csync();
   const long long c_loaded = ph ? clock64() : 0;
   for (int j0 = 0; j0 < nb; j0 += SB) {
     const int jb = min(SB, nb - j0);
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
       ++pq;
       const int type = tk.x & 0xff;
       if (type == DF_DONE) break;
-      if (type == DF_UPD) {
+      if (type == DF_UPD || type == DF_DIAGU) {
         const int i = tk.y, j = tk.z, k0 = tk.w & 0xffff, k1 = tk.w >> 16;
         const int KT = (k1 - k0) * (DF_TILE / BK);
         const double* PA = a.dst + (size_t)i * DF_TILE * a.ld + (size_t)k0 * DF_TILE;
@@ -373,7 +376,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
           }
           mbar_arrive_cp_async(full + s);
         }
-        fetch();
+        if (type == DF_DIAGU) {  // the factorization part re-uses the ring memory: park like a bulk task
+          __syncthreads();
+          fetch();
+          __syncthreads();
+        } else {
+          fetch();
+        }
       } else {
         __syncthreads();  // consumers own the ring memory for the bulk task
         fetch();
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
     long long t_start = 0;
     if (a.tlog && tid == 0) t_start = gtimer();
     const int i = tk.y, j = tk.z;
-    if (type == DF_UPD) {
+    if (type == DF_UPD || type == DF_DIAGU) {
       const int k0 = tk.w & 0xffff, k1 = tk.w >> 16;
       const int KT = (k1 - k0) * (DF_TILE / BK);
       const bool diag = i == j;
@@ -416,7 +425,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
       const int wrow = row0 + wm * 64, wcol = col0 + wn * 32;
       const bool live = !diag || wn <= 2 * wm + 1;  // warp tiles strictly above the diagonal are skipped
       const double* Cin = k0 == 0 ? a.src : a.dst;
-      if (grp == 1) {  // trail group 0 (the producers can always run DF_STAGES slices ahead of this group)
+      if (grp == 1 && type == DF_UPD) {  // trail group 0 (the producers can always run DF_STAGES slices ahead of
+                                         // this group); not in the fused chain task, whose latency matters
         while ((int)(*prog0 - it) < DF_LAG) __nanosleep(200);
       }
       double acc[DF_MI][DF_NI][2];
@@ -463,6 +473,24 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
         if (tid == 0) *prog0 = (int)(it + 1);
       }
       if (a.tlog) c_loop = clock64();
+      if (type == DF_DIAGU) {
+        // fused: the updated diagonal tile goes from the accumulators straight into the shared-memory
+        // tile that DIAG factors (every slice has been consumed once all threads pass the barrier)
+        __syncthreads();
+        if (live) {
+#pragma unroll
+          for (int mi = 0; mi < DF_MI; ++mi) {
+            const int lr = wm * 64 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < DF_NI; ++ni) {
+              const int lc = wn * 32 + ni * 8 + 2 * q;
+              if (lc <= lr) smem[lr * SP + lc] = -acc[mi][ni][0];
+              if (lc + 1 <= lr) smem[lr * SP + lc + 1] = -acc[mi][ni][1];
+            }
+          }
+        }
+        csync();
+      } else {
       if (live) {
 #pragma unroll
         for (int mi = 0; mi < DF_MI; ++mi) {
@@ -497,15 +525,23 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_ldlt_dataflow(DfArgs a) {
         ph[2] = c_stored - c_loop;       // C stores issued
         ph[3] = clock64() - c_stored;    // fence + completion count
       }
-    } else {
-      __syncthreads();  // producers have published and stopped touching the ring
-      if (type == DF_DIAG) df_diag_task(a, smem, j, tid, a.tlog ? a.tlog + (size_t)tnum * 8 + 4 : nullptr);
-      else df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid, a.tlog ? a.tlog + (size_t)tnum * 8 + 4 : nullptr);
+      }  // UPD epilogue
+    }
+    if (type != DF_UPD) {
+      // bulk tasks on the consumer warps (DIAGU arrives here with its tile already in shared memory)
+      if (type != DF_DIAGU) __syncthreads();  // producers have published and stopped touching the ring
+      long long* ph = (a.tlog && type != DF_DIAGU) ? a.tlog + (size_t)tnum * 8 + 4 : nullptr;
+      if (type == DF_TRSM) df_trsm_task(a, smem, i, j, (tk.x >> 8) & 0xff, tid, ph);
+      else df_diag_task(a, smem, j, tid, ph, type == DF_DIAGU);
       csync();
       if (tid == 0) {
         __threadfence();
-        if (type == DF_DIAG) st_release(a.rdy + (size_t)j * a.nt + j, 1);
-        else red_release_add(a.rdy + (size_t)j * a.nt + i, 1);
+        if (type == DF_TRSM) {
+          red_release_add(a.rdy + (size_t)j * a.nt + i, 1);
+        } else {
+          if (type == DF_DIAGU) st_release(a.cnt + (size_t)j * a.nt + j, j);
+          st_release(a.rdy + (size_t)j * a.nt + j, 1);
+        }
       }
       __syncthreads();
     }
@@ -542,8 +578,11 @@ bool dataflow_schedule_check(int N, int workers, int* counts3, double* makespan_
   const DfSchedule s = df_build_schedule(N, m);
   if (counts3) {
     counts3[0] = counts3[1] = counts3[2] = 0;
-    for (const DfTask& t : s.tasks)
-      if ((t.type & 0xff) <= DF_UPD) counts3[t.type & 0xff] += 1;
+    for (const DfTask& t : s.tasks) {
+      const int type = t.type & 0xff;
+      if (type <= DF_UPD) counts3[type] += 1;
+      else if (type == DF_DIAGU) counts3[DF_DIAG] += 1;  // a diagonal factorization with its last updates fused in
+    }
   }
   if (makespan_us) *makespan_us = s.makespan_us;
   if (work_us) *work_us = s.work_us;
@@ -563,6 +602,7 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   m.la = env_int("IPMZ_DF_LA", m.la);
   m.kmax = env_int("IPMZ_DF_KMAX", m.kmax);
   if (m.kmax > 15) m.kmax = 15;  // one lane per flag in wait_deps
+  m.fuse_diag = env_int("IPMZ_DF_FUSE_DIAG", m.fuse_diag ? 1 : 0) != 0;
   m.diag_us = env_double("IPMZ_DF_DIAG_US", m.diag_us);
   m.trsm_us = env_double("IPMZ_DF_TRSM_US", m.trsm_us);
   m.upd_base_us = env_double("IPMZ_DF_UPD_BASE_US", m.upd_base_us);

@@ -5,6 +5,9 @@
 //   DIAG(k)            LDL^T of the diagonal tile (k,k)                    after k updates of (k,k)
 //   TRSM(i,k,h)        64-row half h of tile (i,k):  X (D_k L_kk^T) = A    after DIAG(k) and k updates of (i,k)
 //   UPD(i,j,k0,k1)     C_ij -= sum_{k0<=k<k1} L_ik D_k L_jk^T              after TRSM(i,k), TRSM(j,k), cnt(i,j)==k0
+//   DIAGU(k,k0)        UPD(k,k,k0,k) and DIAG(k) fused: the last updates of a diagonal tile go straight from
+//                      the accumulators into the shared-memory tile that is factored (no round trip
+//                      through global memory and no task switch on the critical chain)
 // The device kernel hands these out through ONE ticket counter, in the order of this list, and
 // each task spins on its dependencies (flags in global memory).  Any topological order is
 // deadlock-free (a waiting ticket only waits on lower tickets, all of which are held by running
@@ -26,7 +29,7 @@ namespace ipmz {
 constexpr int DF_TILE = 128;  // tile edge = panel width
 constexpr int DF_HALF = 64;   // rows per TRSM task
 
-enum DfType { DF_DIAG = 0, DF_TRSM = 1, DF_UPD = 2, DF_DONE = 3 };
+enum DfType { DF_DIAG = 0, DF_TRSM = 1, DF_UPD = 2, DF_DIAGU = 3, DF_DONE = 4 };
 
 struct DfTask {
   int type;  // DfType | half << 8
@@ -36,8 +39,9 @@ struct DfTask {
 
 struct DfModel {
   int workers = 148;
-  double diag_us = 42.0;       // one 128 x 128 LDL^T
-  double trsm_us = 16.0;       // one 64-row half
+  double diag_us = 34.0;       // one 128 x 128 LDL^T
+  double trsm_us = 12.5;       // one 64-row half
+  bool fuse_diag = true;       // emit DIAGU when all remaining updates of a diagonal tile are available
   double upd_base_us = 7.0;    // C tile in/out + pipeline fill (measured: K=1 24.5 us, K=4 77 us)
   double upd_panel_us = 17.5;  // 128 x 128 x 128 on one SM at ~95 % of its DMMA rate
   int kb = 4;                  // panels accumulated before a non-urgent tile is updated
@@ -100,6 +104,15 @@ inline DfSchedule df_build_schedule(int N, const DfModel& m) {
       return;
     }
     int nk;
+    if (m.fuse_diag && i == j && rows_of(i) == DF_TILE && !queued[t]) {
+      // every remaining panel of this diagonal tile is there: update and factor in one task
+      nk = avail_k(i, j);
+      if (nk > 0 && nk == j - cnt[t]) {
+        queued[t] = 1;
+        ready.push(Cand{key_of(j, 0, i), DF_DIAGU, i, j, 0});
+        return;
+      }
+    }
     if (!queued[t] && upd_eligible(i, j, nk)) {
       queued[t] = 1;
       ready.push(Cand{key_of(j, 2, i), DF_UPD, i, j, 0});
@@ -115,7 +128,12 @@ inline DfSchedule df_build_schedule(int N, const DfModel& m) {
   auto complete = [&](int idx) {
     const DfTask& tk = out.tasks[idx];
     const int type = tk.type & 0xff, i = tk.i, j = tk.j;
-    if (type == DF_DIAG) {
+    if (type == DF_DIAG || type == DF_DIAGU) {
+      if (type == DF_DIAGU) {
+        cnt[(size_t)i * nt + j] = j;
+        busy[(size_t)i * nt + j] = 0;
+        final_pushed[(size_t)i * nt + j] = 1;
+      }
       diag_done[j] = 1;
       rdy[(size_t)j * nt + j] = 1;
       for (int r = j + 1; r < nt; ++r) touch(r, j);
@@ -161,6 +179,20 @@ inline DfSchedule df_build_schedule(int N, const DfModel& m) {
         busy[t] = 1;
         tk = DfTask{DF_UPD, c.i, c.j, cnt[t] | ((cnt[t] + nk) << 16)};
         dur = m.upd_base_us + m.upd_panel_us * nk;
+      } else if (c.kind == DF_DIAGU) {
+        const size_t t = (size_t)c.i * nt + c.j;
+        queued[t] = 0;
+        const int nk = busy[t] ? 0 : avail_k(c.i, c.j);
+        if (nk <= 0 || nk != c.j - cnt[t]) {  // stale: re-examine the tile
+          touch(c.i, c.j);
+          continue;
+        }
+        busy[t] = 1;
+        tk = DfTask{DF_DIAGU, c.i, c.j, cnt[t] | (c.j << 16)};
+        dur = 0.5 * m.upd_base_us + m.upd_panel_us * nk + m.diag_us;
+        front = c.j;
+        for (int col = front + 1; col <= std::min(nt - 1, front + m.la); ++col)
+          for (int r = col; r < nt; ++r) touch(r, col);
       } else if (c.kind == DF_TRSM) {
         tk = DfTask{DF_TRSM | (c.h << 8), c.i, c.j, 0};
         dur = m.trsm_us;
@@ -206,12 +238,17 @@ inline bool df_validate_schedule(int N, const DfSchedule& s) {
       if (i == j || !rdy[(size_t)j * nt + j] || cnt[(size_t)i * nt + j] != j) return false;
       if (++rdy[(size_t)j * nt + i] > need_of(i)) return false;
       fin[(size_t)i * nt + j] = 1;
-    } else if (type == DF_UPD) {
+    } else if (type == DF_UPD || type == DF_DIAGU) {
       const int k0 = tk.k01 & 0xffff, k1 = tk.k01 >> 16;
       if (k0 >= k1 || k1 > j || cnt[(size_t)i * nt + j] != k0) return false;
       for (int k = k0; k < k1; ++k)
         if (rdy[(size_t)k * nt + i] != need_of(i) || rdy[(size_t)k * nt + j] != need_of(j)) return false;
       cnt[(size_t)i * nt + j] = k1;
+      if (type == DF_DIAGU) {
+        if (i != j || k1 != j || rows_of(i) != DF_TILE || rdy[(size_t)j * nt + j]) return false;
+        rdy[(size_t)j * nt + j] = 1;
+        fin[(size_t)i * nt + j] = 1;
+      }
     } else {
       return false;
     }

@@ -22,7 +22,7 @@ t0 = log[:, 0].min(); st = (log[:, 0] - t0) * 1e-3; en = (log[:, 1] - t0) * 1e-3
 typ = log[:, 3] & 0xff; kw = (log[:, 3] >> 32); K = (kw >> 16) - (kw & 0xffff)
 print("makespan us %.1f" % en.max())
 dur = en - st
-for t, name in ((0, "DIAG"), (1, "TRSM"), (2, "UPD")):
+for t, name in ((0, "DIAG"), (3, "DIAGU"), (1, "TRSM"), (2, "UPD")):
     m = typ == t
     if m.any():
         print("%s: n=%d mean %.2f us  p10 %.2f p50 %.2f p90 %.2f max %.2f  total %.1f ms-SM" % (
@@ -59,7 +59,12 @@ for a, b_ in zip(order[:-1], order[1:]):
 gaps = np.array(gaps)
 print("gaps between tasks on an SM: mean %.2f us p50 %.2f p90 %.2f p99 %.2f max %.1f; total %.1f ms-SM" % (
     gaps.mean(), *np.percentile(gaps, [50, 90, 99]), gaps.max(), gaps.sum() * 1e-3))
-d = np.where(typ == 0)[0]
+fu = typ == 3
+for k in range(1, 9):
+    mk = fu & (K == k)
+    if mk.any():
+        print("  DIAGU K=%d: n=%d median %.2f us" % (k, mk.sum(), np.median(dur[mk])))
+d = np.where((typ == 0) | (typ == 3))[0]
 ds = st[d]; print("DIAG start times (us) every 8th:", np.round(np.sort(ds)[::8], 0))
 if len(sys.argv) > 2:
     np.save(sys.argv[2], log)
