@@ -176,9 +176,20 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
     }
   }
   const long long c_factored = ph ? clock64() : 0;
+  // strict lower part = L, diagonal = pivots; 16-byte stores (row bases and even columns are aligned)
+#pragma unroll 4
   for (int r = warp; r < nb; r += DF_CONSUMERS) {
-    for (int c = lane; c < r; c += 32) O[(size_t)r * a.ld + c] = S[r * SP + c];
-    if (lane == 0) O[(size_t)r * a.ld + r] = dsm[r];
+    const double dr = dsm[r];
+#pragma unroll
+    for (int h = 0; h < NB / 64; ++h) {
+      const int c = 2 * lane + 64 * h;
+      if (c > r) continue;
+      const double2 v = *reinterpret_cast<const double2*>(S + r * SP + c);
+      double* o = O + (size_t)r * a.ld + c;
+      if (c + 1 < r) *reinterpret_cast<double2*>(o) = v;
+      else if (c + 1 == r) *reinterpret_cast<double2*>(o) = make_double2(v.x, dr);
+      else *o = dr;  // c == r
+    }
   }
   for (int t = tid; t < nb; t += DF_CTHREADS) a.Dg[k0 + t] = dsm[t];
   if (ph && tid == 0) {
@@ -220,15 +231,8 @@ __device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i,
   double* Wout = a.W + (size_t)r0 * a.ld + k0;
 
   const long long c_begin = ph ? clock64() : 0;
-  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, NB, NB, tid);
-  cp_async_commit();
-  const long long c_issued = ph ? clock64() : 0;
-  for (int t = tid; t < NB; t += DF_CTHREADS) dsm[t] = __ldcg(a.Dg + k0 + t);
-  {
-    const double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
-    for (int t = tid; t < 16 * INV_BLK; t += DF_CTHREADS) binv[t] = __ldcg(gi + t);
-  }
-  // this lane's part of the warp's 8 rows, in accumulator layout (row g, columns 8b + 2q, +1)
+  // this lane's part of the warp's 8 rows, in accumulator layout (row g, columns 8b + 2q, +1): the loads
+  // are issued first, their latency hides behind the cp.async issue loop of L_kk
   const int row = r0 + 8 * warp + g;
   const bool row_ok = row < a.N;
   double acc[16][2];
@@ -238,6 +242,14 @@ __device__ __forceinline__ void df_trsm_task(const DfArgs& a, double* sm, int i,
     if (row_ok) v = __ldcg(reinterpret_cast<const double2*>(Ain + (size_t)(8 * warp + g) * a.ld + 8 * b + 2 * q));
     acc[b][0] = v.x;
     acc[b][1] = v.y;
+  }
+  const long long c_issued = ph ? clock64() : 0;
+  async_block_load<true, DF_CTHREADS>(S, Lkk, a.ld, NB, NB, tid);
+  cp_async_commit();
+  for (int t = tid; t < NB; t += DF_CTHREADS) dsm[t] = __ldcg(a.Dg + k0 + t);
+  {
+    const double* gi = a.Ginv + (size_t)(k0 / 8) * INV_BLK;
+    for (int t = tid; t < 16 * INV_BLK; t += DF_CTHREADS) binv[t] = __ldcg(gi + t);
   }
   const long long c_acc = ph ? clock64() : 0;
   cp_async_wait<0>();

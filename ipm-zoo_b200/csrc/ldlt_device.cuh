@@ -31,6 +31,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // flight at once (a plain load/store loop would serialise on the L2 latency).
 template <bool LOWER, int NT = 256>
 __device__ __forceinline__ void async_block_load(double* S, const double* A, int ld, int rows, int cols, int tid) {
+  if (cols == NB) {  // full-width block: 64 chunks per row, index arithmetic by shifts
+    for (int idx = tid; idx < rows * (NB / 2); idx += NT) {
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      if (LOWER && c > r) continue;
+      cp_async16(S + r * SP + c, A + (size_t)r * ld + c, 16);
+    }
+    return;
+  }
   const int half = (cols + 1) >> 1;
   for (int idx = tid; idx < rows * half; idx += NT) {
     const int r = idx / half, c = (idx - r * half) * 2;
