@@ -157,6 +157,10 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
     csync();
   }
   const long long c_loaded = ph ? clock64() : 0;
+  // Look-ahead inside the tile: after the 32 x 32 sub-block j0 is factored, all warps first bring the NEXT
+  // diagonal sub-block up to date (its 32 rows of the panel solve + its own update); then warp 0 factors it
+  // while warps 1-7 solve and update the rest of the trailing part of step j0.  The dependent chain of the
+  // tile is 4 one-warp factorizations + 3 short critical parts instead of 4 full solve/update rounds.
   for (int j0 = 0; j0 < nb; j0 += SB) {
     const int jb = min(SB, nb - j0);
     if (warp == 0) {
@@ -164,17 +168,32 @@ __device__ __forceinline__ void df_diag_task(const DfArgs& a, double* sm, int k,
       warp_ldlt32(S, j0, jb, dsm, dinv, colbuf, binv + (j0 / SB) * INV_SUB, lane);
       if (ph) c_ldlt += clock64() - c0;
     }
-    csync();
+    csync();  // L32 / inverse blocks of j0 are there, and every update of step j0 - 32 has landed
     const int base = j0 + jb, rem = nb - base;
     if (rem > 0) {
-      panel_solve32(S + base * SP + j0, rem, S + j0 * SP + j0, dsm + j0, binv + (j0 / SB) * INV_SUB, warp, lane,
-                    DF_CONSUMERS);
+      const double* Lb = S + j0 * SP + j0;
+      const double* bi = binv + (j0 / SB) * INV_SUB;
+      const int crit = min(SB, rem);  // rows / columns of the next diagonal sub-block
+      panel_solve32(S + base * SP + j0, crit, Lb, dsm + j0, bi, warp, lane, DF_CONSUMERS);
       csync();
-      smem_update<true>(S + base * SP + base, S + base * SP + j0, S + base * SP + j0, dsm + j0, rem, rem, jb, warp,
+      smem_update<true>(S + base * SP + base, S + base * SP + j0, S + base * SP + j0, dsm + j0, crit, crit, jb, warp,
                         lane, DF_CONSUMERS);
       csync();
+      if (warp > 0 && rem > crit) {
+        // the rest of step j0 on warps 1-7 (warp 0 is already factoring the next sub-block)
+        const int rest = rem - crit, b2 = base + crit;
+        panel_solve32(S + b2 * SP + j0, rest, Lb, dsm + j0, bi, warp - 1, lane, DF_CONSUMERS - 1);
+        bar_named(3, DF_CTHREADS - 32);
+        // rectangular part: rows >= b2, the columns of the next sub-block
+        smem_update<false>(S + b2 * SP + base, S + b2 * SP + j0, S + base * SP + j0, dsm + j0, rest, crit, jb, warp - 1,
+                           lane, DF_CONSUMERS - 1);
+        // lower triangle from b2 on
+        smem_update<true>(S + b2 * SP + b2, S + b2 * SP + j0, S + b2 * SP + j0, dsm + j0, rest, rest, jb, warp - 1, lane,
+                          DF_CONSUMERS - 1);
+      }
     }
   }
+  csync();
   const long long c_factored = ph ? clock64() : 0;
   // strict lower part = L, diagonal = pivots; 16-byte stores (row bases and even columns are aligned)
 #pragma unroll 4
