@@ -208,13 +208,19 @@ __global__ void __launch_bounds__(256, 4) k_trsv_small(TrsvArgs a) {
     double s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.0;
-    for (int c0 = 0; c0 < R0; c0 += 32) {
-      const double xc = sx[c0 + lane];
+    // two 32-column chunks per trip: 16 independent loads in flight per lane (the loop is latency bound)
+    for (int c0 = 0; c0 < R0; c0 += 64) {
+      const double xa = sx[c0 + lane], xb = sx[c0 + 32 + lane];
+      double la[8], lb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = 8 * warp + i;
-        if (row < nr) s[i] = fma(K[(size_t)(R0 + row) * a.ld + c0 + lane], xc, s[i]);
+        const double* Kr = K + (size_t)(R0 + row) * a.ld + c0 + lane;
+        la[i] = row < nr ? Kr[0] : 0.0;
+        lb[i] = row < nr ? Kr[32] : 0.0;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = fma(lb[i], xb, fma(la[i], xa, s[i]));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -251,7 +257,20 @@ __global__ void __launch_bounds__(256, 4) k_trsv_small(TrsvArgs a) {
     // column R0 + c against the finished rows below the block, rows split over the 4 thread groups
     double sacc = 0.0;
     if (c < nr) {
-      for (int row = R0 + TB + grp; row < N; row += 4) sacc = fma(K[(size_t)row * a.ld + R0 + c], sx[row], sacc);
+      // 8 independent loads / partial sums per trip (latency bound otherwise)
+      double p8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) p8[u] = 0.0;
+      int row = R0 + TB + grp;
+      for (; row + 28 < N; row += 32) {
+        double lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) lv[u] = K[(size_t)(row + 4 * u) * a.ld + R0 + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p8[u] = fma(lv[u], sx[row + 4 * u], p8[u]);
+      }
+      for (; row < N; row += 4) p8[0] = fma(K[(size_t)row * a.ld + R0 + c], sx[row], p8[0]);
+      sacc = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
     }
     part[grp][c] = sacc;
     __syncthreads();
