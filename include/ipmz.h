@@ -174,6 +174,12 @@ int ipmz_batch_destroy(ipmz_batch_handle h);
 int ipmz_batch_upload(ipmz_batch_handle h, const ipmz_problem* data);
 int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem /* count entries or NULL */,
                      double* ms_total);
+/* g batches of ONE device solved concurrently, one host thread + CUDA stream per handle (latency-bound
+ * kernels of one sub-batch overlap throughput-bound kernels of another); ms_total = device time from the
+ * earliest start to the latest end. Per-problem results: ipmz_batch_get_x / _get_iterates per handle. */
+int ipmz_batch_solve_group(int g, ipmz_batch_handle* handles, double* ms_total);
+/* Per-problem outcome (iterations, converged, f, res, mu) of the handle's last solve; count entries. */
+int ipmz_batch_results(ipmz_batch_handle h, ipmz_result* per_problem);
 int ipmz_batch_get_iterates(ipmz_batch_handle h, double* packed /* count x iterate_len */);
 int ipmz_batch_get_x(ipmz_batch_handle h, double* x /* count x n */);
 

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_factor_run", "ipmz_factor_profile", "ipmz_factor_get_solution", "ipmz_factor_get_ld",
     "ipmz_factor_info", "ipmz_schedule_check",
     "ipmz_batch_create", "ipmz_batch_destroy", "ipmz_batch_upload", "ipmz_batch_solve",
-    "ipmz_batch_get_iterates", "ipmz_batch_get_x",
+    "ipmz_batch_get_iterates", "ipmz_batch_get_x", "ipmz_batch_solve_group", "ipmz_batch_results",
 ]
 
 
@@ -110,6 +110,8 @@ def lib():
         L.ipmz_batch_solve.argtypes = [vp, C.POINTER(_Result), dp]
         L.ipmz_batch_get_iterates.argtypes = [vp, dp]
         L.ipmz_batch_get_x.argtypes = [vp, dp]
+        L.ipmz_batch_solve_group.argtypes = [C.c_int, C.POINTER(vp), dp]
+        L.ipmz_batch_results.argtypes = [vp, C.POINTER(_Result)]
         _lib = L
     return _lib
 
@@ -306,6 +308,12 @@ class BatchSolver:
         _check(lib().ipmz_batch_solve(self._h, arr, C.byref(ms)))
         return ([Result(r) for r in arr] if per_problem else None), ms.value
 
+    def results(self):
+        """Per-problem outcome of the last solve (also after solve_group)."""
+        arr = (_Result * self.count)()
+        _check(lib().ipmz_batch_results(self._h, arr))
+        return [Result(r) for r in arr]
+
     def x(self, out=None):
         out = np.zeros((self.count, self.p.n)) if out is None else out
         _check(lib().ipmz_batch_get_x(self._h, _ptr(out)))
@@ -315,6 +323,16 @@ class BatchSolver:
         out = np.zeros((self.count, self.p.iterate_len))
         _check(lib().ipmz_batch_get_iterates(self._h, _ptr(out)))
         return out
+
+
+def solve_group(solvers):
+    """Solve several BatchSolver handles of one device concurrently (one host thread + CUDA stream each,
+    native threads inside the library); returns the device time in ms from the earliest start to the
+    latest end.  Per-problem outcomes: BatchSolver.results()."""
+    hs = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+    ms = C.c_double()
+    _check(lib().ipmz_batch_solve_group(len(solvers), hs, C.byref(ms)))
+    return ms.value
 
 
 class Factor:

@@ -3,13 +3,15 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include <atomic>
+
 #include "ipmz_device.cuh"
 
 namespace ipmz {
 
 // every launcher bumps this (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_launch_count;  // several handles may run on their own host threads
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // ---- vector_kernels.cu ----
 void launch_matvec(cudaStream_t st, int nslots, const int* active, const double* A, int lda, size_t sA,

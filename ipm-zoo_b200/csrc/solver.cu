@@ -13,6 +13,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ipmz.h"
@@ -21,7 +22,7 @@
 
 namespace ipmz {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 static thread_local std::string g_err;
 
 static int fail(int code, const std::string& msg) {
@@ -490,7 +491,7 @@ void ipmz_default_options(ipmz_options* opt) {
   opt->refine_steps = -1;
 }
 
-unsigned long long ipmz_launch_count(void) { return g_launch_count; }
+unsigned long long ipmz_launch_count(void) { return g_launch_count.load(); }
 
 int ipmz_iterate_len(const ipmz_problem* p) { return 5 * p->n + 6 * p->m_ineq + 6 * p->m_eq; }
 
@@ -704,6 +705,46 @@ int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem, double* ms_t
   if (ms_total) *ms_total = ms;
   if (per_problem)
     for (int q = 0; q < w.count; ++q) fill_result(w, q, per_problem + q, ms);
+  return IPMZ_OK;
+}
+
+// Several batches of one device concurrently: one host thread and one CUDA stream per handle, so the
+// latency-bound kernels of one sub-batch overlap the throughput-bound kernels of another (SURVEY 8e:
+// "one host thread + CUDA stream set per device").  ms_total = device time from the earliest start to the
+// latest end over the handles' streams.
+int ipmz_batch_solve_group(int g, ipmz_batch_handle* hs, double* ms_total) {
+  if (g <= 0 || !hs) return fail(IPMZ_ERR_ARG, "bad argument");
+  for (int i = 0; i < g; ++i)
+    if (!hs[i]) return fail(IPMZ_ERR_ARG, "null handle");
+  std::vector<int> rcs(g, 0);
+  std::vector<std::string> errs(g);
+  std::vector<std::thread> th;
+  for (int i = 0; i < g; ++i)
+    th.emplace_back([&, i]() {
+      double ms = 0.0;
+      rcs[i] = run_ipm(*hs[i]->w, &ms);
+      if (rcs[i]) errs[i] = g_err;
+      hs[i]->last_ms = ms;
+    });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < g; ++i)
+    if (rcs[i]) return fail(rcs[i], errs[i]);
+  if (ensure_device(hs[0]->w->device)) return IPMZ_ERR_CUDA;
+  float best = 0.f;
+  for (int i = 0; i < g; ++i)
+    for (int j = 0; j < g; ++j) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, hs[i]->w->ev0, hs[j]->w->ev1));
+      if (ms > best) best = ms;
+    }
+  if (ms_total) *ms_total = best;
+  return IPMZ_OK;
+}
+
+// iterations / converged / f / res / mu of every problem of the handle's last solve
+int ipmz_batch_results(ipmz_batch_handle h, ipmz_result* per_problem) {
+  if (!h || !per_problem) return fail(IPMZ_ERR_ARG, "null argument");
+  for (int q = 0; q < h->w->count; ++q) fill_result(*h->w, q, per_problem + q, h->last_ms);
   return IPMZ_OK;
 }
 

@@ -217,3 +217,30 @@ def test_error_conventions(z):
     with pytest.raises(z.IpmzError) as e:
         z.Solver(zp)
     assert e.value.code == 4
+
+
+def test_batch_solve_group_matches_single_batch():
+    """ipmz_batch_solve_group (several handles of one device on their own host threads / streams) gives
+    exactly the results of one batch over the same problems."""
+    import ipm_zoo_b200 as z
+    import problems as P
+    n, m, count = 48, 20, 12
+    probs = [P.ineq_box(n, m, 700 + i) for i in range(count)]
+    st = lambda key, lo, hi: np.stack([getattr(q, key) for q in probs[lo:hi]])
+    mk = lambda lo, hi: z.Problem(st("Q", lo, hi), st("c", lo, hi), st("A", lo, hi), st("l_A", lo, hi),
+                                  st("u_A", lo, hi), None, None, st("l_x", lo, hi), st("u_x", lo, hi))
+    one = z.BatchSolver(mk(0, count), count)
+    res, _ = one.solve()
+    x_one = one.x()
+    one.close()
+    cuts = [0, 5, 9, 12]
+    subs = [z.BatchSolver(mk(cuts[g], cuts[g + 1]), cuts[g + 1] - cuts[g]) for g in range(3)]
+    ms = z.solve_group(subs)
+    assert ms > 0
+    got = [r for s in subs for r in s.results()]
+    x_grp = np.concatenate([s.x() for s in subs])
+    for s in subs:
+        s.close()
+    assert [r.iterations for r in got] == [r.iterations for r in res]
+    assert all(r.converged for r in got)
+    assert np.array_equal(x_grp, x_one)
