@@ -603,8 +603,16 @@ static double env_double(const char* name, double dflt) {
   return s ? atof(s) : dflt;
 }
 
+// Large matrices have enough bulk work to group more panels per update task (less C traffic, fewer task
+// switches); below ~48 tile rows the critical chain dominates and small groups keep it fed
+// (n=8192: 7.22 -> 6.97 ms, n=12288: 21.3 -> 21.0 ms; n=4096: 2.03 ms with the small groups vs 2.22).
+static void df_size_policy(int N, DfModel& m) {
+  if ((N + DF_TILE - 1) / DF_TILE >= 48) { m.kb = 8; m.kmax = 15; m.la = 3; }
+}
+
 bool dataflow_schedule_check(int N, int workers, int* counts3, double* makespan_us, double* work_us) {
   DfModel m;
+  df_size_policy(N, m);
   if (workers > 0) m.workers = workers;
   const DfSchedule s = df_build_schedule(N, m);
   if (counts3) {
@@ -629,6 +637,7 @@ int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   DfModel m;
   m.workers = nsm;
+  df_size_policy(N, m);
   m.kb = env_int("IPMZ_DF_KB", m.kb);
   m.la = env_int("IPMZ_DF_LA", m.la);
   m.kmax = env_int("IPMZ_DF_KMAX", m.kmax);
