@@ -154,7 +154,7 @@ int ipmz_factor_run(ipmz_factor_handle h, int reps, int nrhs, double* ms_total);
  * flops and launch count of the trailing updates (the roofline numerator of bench.py). */
 int ipmz_factor_profile(ipmz_factor_handle h, double* ms3, double* flops_syrk, int* n_syrk);
 /* Which factorization path the handle runs: *dataflow = 1 for the persistent single-launch
- * dataflow kernel (n >= IPMZ_DATAFLOW_MIN_N, default 2048), with its task count and the
+ * dataflow kernel (n >= IPMZ_DATAFLOW_MIN_N, default 512), with its task count and the
  * makespan of the host-simulated list schedule; 0 for the multi-kernel schedule. */
 int ipmz_factor_info(ipmz_factor_handle h, int* dataflow, int* ntasks, double* simulated_us);
 /* Host-only (no GPU needed): build the dataflow task list of an n x n matrix for `workers` SMs and

@@ -628,7 +628,7 @@ bool dataflow_schedule_check(int N, int workers, int* counts3, double* makespan_
   return df_validate_schedule(N, s);
 }
 
-int dataflow_min_n() { return env_int("IPMZ_DATAFLOW_MIN_N", 2048); }
+int dataflow_min_n() { return env_int("IPMZ_DATAFLOW_MIN_N", 512); }
 
 int dataflow_plan_create(DataflowPlan** out, int N, int ld) {
   *out = nullptr;

@@ -219,7 +219,9 @@ int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double*
   if (e == cudaSuccess) e = cudaMemcpy(h->Dg, D, sizeof(double) * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->x, b, sizeof(double) * n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    const FactorPlan fp = plan(h);
+    FactorPlan fp = plan(h);
+    fp.df = nullptr;  // L and D come from the caller: the streaming solve needs the 8 x 8 inverse blocks that
+                      // only a factorization on this handle produces -> block-row sweeps on L, D alone
     launch_ldlt_solve(h->st, fp, h->L, h->Dg, h->x, (size_t)h->ld, h->tw);
     e = cudaStreamSynchronize(h->st);
   }
