@@ -67,92 +67,79 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
-        self.nv, self.h, self.stop_flag, self.samples = None, None, False, []
-        try:  # NVML in-process: a sample every millisecond (the timed region is tens of ms)
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[device]) if vis and vis.split(",")[device].strip().isdigit() else device
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.nv = pynvml
-        except Exception:
-            self.nv = None
-
-    def _poll(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                try:
-                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((sm, rs))
-            except Exception:
-                pass
-            time.sleep(0.001)
-
-    def start(self):
-        if self.nv is not None:
-            self.stop_flag = False
-            self.th = threading.Thread(target=self._poll, daemon=True)
-            self.th.start()
-            return
+    POLLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+try:
+    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+except Exception:
+    mx = -1
+print("max", mx, flush=True)
+while True:
+    try:
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        print("%.6f %d %d" % (time.time(), sm, rs), flush=True)
+    except Exception:
+        pass
+    time.sleep(0.001)
+"""
+
+    def __init__(self, device):
+        # NVML polled every millisecond by a separate process (no GIL contention with the bench thread);
+        # start() / stop() only mark the time window whose samples are reported
+        self.device, self.rows, self.proc, self.mx = device, [], None, None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device
+        if vis:
+            parts = vis.split(",")
+            if device < len(parts) and parts[device].strip().isdigit():
+                idx = int(parts[device])
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", self.POLLER, str(idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+        self.t0 = self.t1 = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            t = line.split()
+            if t and t[0] == "max":
+                self.mx = int(t[1])
+            elif len(t) == 3:
+                self.rows.append((float(t[0]), int(t[1]), int(t[2])))
+
+    def start(self):
+        self.t0 = time.time()
 
     def stop(self):
-        if self.nv is not None:
-            nv = self.nv
-            self.stop_flag = True
-            self.th.join(timeout=2)
-            sm = [x[0] for x in self.samples]
-            bits = 0
-            for x in self.samples:
-                bits |= int(x[1])
-            names = [("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
-                     ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
-                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
-                     ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")]
-            reasons = [nm for nm, attr in names if bits & int(getattr(nv, attr, 0))]
-            try:
-                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
-            except Exception:
-                mx = None
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                    "reasons": sorted(reasons), "how": "NVML polled every ms during the timed region"}
+        self.t1 = time.time()
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML poller unavailable"]}
+        time.sleep(0.01)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[4 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        rows = [r for r in self.rows if self.t0 <= r[0] <= self.t1]
+        sm = [r[1] for r in rows]
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        reasons = [nm for nm, bit in names if bits & bit]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx if self.mx and self.mx > 0 else None,
+                "samples": len(sm), "reasons": sorted(reasons),
+                "how": "NVML polled every ms by a helper process; samples inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -258,6 +245,7 @@ def ours(args):
     s = z.Solver(prob, opt)
     Kc = s.assemble()
     s.close()
+    sampler = ClockSampler(local)  # helper process: polling long before the timed region starts
     fac = z.Factor(N, device=local)
     fac.set_matrix(Kc)
     rhs = np.random.default_rng(11).standard_normal(N)
@@ -267,7 +255,6 @@ def ours(args):
     x = fac.solution()
     resid = float(np.max(np.abs(Kc @ x - rhs)) / np.max(np.abs(rhs)))
     launches0 = z.launch_count()
-    sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
