@@ -5,10 +5,10 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="${EXTRA_NVCC_FLAGS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++"
 mkdir -p "$HERE/csrc/_obj"
-for f in vector_kernels assemble factor dataflow trsv solver linear_solvers; do
+for f in vector_kernels assemble factor dataflow dataflow_tma trsv solver linear_solvers; do
   if [ ! -f "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/$f.cu" -nt "$HERE/csrc/_obj/$f.o" ] || \
      [ "$HERE/csrc/ipmz_device.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ldlt_device.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || \
-     [ "$HERE/csrc/ldlt_schedule.hpp" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ipmz_kernels.h" -nt "$HERE/csrc/_obj/$f.o" ] || \
+     [ "$HERE/csrc/ldlt_schedule.hpp" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/dataflow_kernel.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ipmz_kernels.h" -nt "$HERE/csrc/_obj/$f.o" ] || \
      [ "$HERE/../include/ipmz.h" -nt "$HERE/csrc/_obj/$f.o" ]; then
     $NVCC $FLAGS ${VERBOSE:+-Xptxas -v} -c "$HERE/csrc/$f.cu" -o "$HERE/csrc/_obj/$f.o" &
   fi

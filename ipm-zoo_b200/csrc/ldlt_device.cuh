@@ -303,5 +303,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 
+// Bounded wait: gives up after ~2^26 polls (seconds) and raises *sticky, so that a transfer that never
+// completes (a faulting bulk copy, a protocol bug) ends the kernel with an error instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity, int* sticky) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  if (sticky) atomicExch(sticky, 1);
+}
+
 }  // namespace
 }  // namespace ipmz
