@@ -55,7 +55,10 @@ enum { IPMZ_BOUNDS_NONE = 0, IPMZ_BOUNDS_LOWER = 1, IPMZ_BOUNDS_UPPER = 2, IPMZ_
 /* Which reduction of the Newton system is assembled and factorized (north_star). */
 enum {
   IPMZ_REDUCTION_AUGMENTED = 0, /* quasi-definite [[Hx, M^T],[M, -W^-1]], LDL^T, N = n+m   */
-  IPMZ_REDUCTION_NORMAL = 1     /* primal condensed Hx + M^T W M, root-free Cholesky, N = n */
+  IPMZ_REDUCTION_NORMAL = 1,    /* primal condensed Hx + M^T W M, root-free Cholesky, N = n */
+  IPMZ_REDUCTION_FULL = 2       /* un-reduced Newton system (SymbolicOptimization.cpp:417-433), symmetrised and
+                                   ordered so that unpivoted LDL^T performs the reference's block elimination;
+                                   N = n + 2m + 2n*(sides of the box) + 2m*(sides of the rows) <= 5n + 6m */
 };
 
 typedef struct {
@@ -132,7 +135,8 @@ int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* 
 int ipmz_get_trace(ipmz_handle h, int cap, double* f, double* res, double* mu, double* step_aff,
                    double* step_cor, double* alpha_aff, double* sigma, double* alpha);
 /* Dense copy (N x N, row-major, full symmetric) of the reduced matrix assembled at the
- * current iterate, N = n+m (augmented) or n (normal). */
+ * current iterate, N = n+m (augmented), n (normal) or the full-system size (full; unknowns ordered
+ * dy dz dsl dsu | dlam_y dlam_z dlam_l dlam_u | ds | dx | dlam, absent groups skipped). */
 int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out);
 
 /* ---- mirror of LinearSolvers (host buffers in/out, as the reference's free functions) ---- */

@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-AUGMENTED, NORMAL = 0, 1
+AUGMENTED, NORMAL, FULL = 0, 1, 2
 NONE, LOWER, UPPER, BOTH = 0, 1, 2, 3
 dp = C.POINTER(C.c_double)
 
@@ -273,7 +273,7 @@ class Solver:
                     step_cor=None if sc is None else sc[:iterations])
 
     def assemble(self):
-        N = self.p.N
+        N = self.p.N if self.opt.c.reduction != FULL else 5 * self.p.n + 6 * (self.p.N - self.p.n)
         K = np.zeros((N, N))
         nout = C.c_int()
         _check(lib().ipmz_assemble(self._h, _ptr(K), C.byref(nout)))

@@ -37,6 +37,39 @@ struct Shape {
   int ncomp;         // number of complementarity entries (denominator of mu)
 };
 
+// FULL reduction (un-reduced Newton system, SymbolicOptimization.cpp:417-433): unknowns in the order
+// the reference's block elimination removes them (complementarity slacks first, x and lambda last), so
+// that the unpivoted LDL^T of the symmetrised matrix performs exactly that elimination and every
+// pivot is nonzero:
+//   dy dz dsl dsu | dlam_y dlam_z dlam_l dlam_u | ds | dx | dlam
+// Variable-bound groups exist only when the bound side does (n entries each); the row-slack groups
+// exist when any row has that side (m entries; rows without it are decoupled identity rows).
+struct FullLayout {
+  int oy, oz, osl, osu, oly, olz, oll, olu, os, ox, olam, N;
+  int hasl, hasu;
+};
+
+static inline FullLayout full_layout(const Shape& s) {
+  FullLayout f;
+  const int me = s.m - s.mi;
+  f.hasl = (s.m > 0) && (s.ilo || me > 0);
+  f.hasu = (s.m > 0) && (s.iup || me > 0);
+  int o = 0;
+  f.oy = o;  o += s.ylo ? s.n : 0;
+  f.oz = o;  o += s.zup ? s.n : 0;
+  f.osl = o; o += f.hasl ? s.m : 0;
+  f.osu = o; o += f.hasu ? s.m : 0;
+  f.oly = o; o += s.ylo ? s.n : 0;
+  f.olz = o; o += s.zup ? s.n : 0;
+  f.oll = o; o += f.hasl ? s.m : 0;
+  f.olu = o; o += f.hasu ? s.m : 0;
+  f.os = o;  o += s.m;
+  f.ox = o;  o += s.n;
+  f.olam = o; o += s.m;
+  f.N = o;
+  return f;
+}
+
 // Per-problem scalars, device-resident across the whole solve.
 struct Scal {
   double f, res, mu;
@@ -65,7 +98,9 @@ struct View {
   double* K;               // reduced matrix / factor
   double* Dg;              // pivots
   size_t sK;
-  int ldk, N, normal;      // N = n+m (augmented) or n (normal)
+  int ldk, N, normal;      // N = n+m (augmented), n (normal) or FullLayout::N (full)
+  int full;                // 1: un-reduced system in the FullLayout order
+  FullLayout fl;
   Scal* sc;
   const int* active;       // slot -> problem index (nullptr: identity)
   double* partials;        // [slots][maxblk][8] reduction scratch

@@ -36,6 +36,11 @@ void launch_assemble(cudaStream_t st, const View& v, int nslots);
 void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
                        size_t sM, int rows, int cols, const double* d, size_t sd);
 
+// ---- full_system.cu: the un-reduced Newton system in the FullLayout order ----
+void launch_assemble_full(cudaStream_t st, const View& v, int nslots);
+void launch_full_rhs(cudaStream_t st, const View& v, int nslots);             // R, V -> sol
+void launch_full_unpack(cudaStream_t st, const View& v, int nslots, int mode);  // sol -> DA / D, step length
+
 // ---- factor.cu ----
 // Side stream + events of the look-ahead schedule of launch_ldlt (one per handle).
 struct LookAhead {

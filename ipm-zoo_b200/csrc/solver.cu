@@ -203,7 +203,8 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (count <= 0) return fail(IPMZ_ERR_ARG, "count must be positive");
   ipmz_options opt;
   if (opt_in) opt = *opt_in; else ipmz_default_options(&opt);
-  if (opt.reduction != IPMZ_REDUCTION_AUGMENTED && opt.reduction != IPMZ_REDUCTION_NORMAL)
+  if (opt.reduction != IPMZ_REDUCTION_AUGMENTED && opt.reduction != IPMZ_REDUCTION_NORMAL &&
+      opt.reduction != IPMZ_REDUCTION_FULL)
     return fail(IPMZ_ERR_ARG, "unknown reduction");
   if ((rc = ensure_device(opt.device))) return rc;
 
@@ -221,13 +222,15 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
     return fail(IPMZ_ERR_INDEFINITE, "equality rows given but Settings::equalities is off");
   w->Naug = s.n + s.m;
   v.normal = (opt.reduction == IPMZ_REDUCTION_NORMAL) ? 1 : 0;
-  v.N = v.normal ? s.n : w->Naug;
+  v.full = (opt.reduction == IPMZ_REDUCTION_FULL) ? 1 : 0;
+  v.fl = full_layout(s);
+  v.N = v.normal ? s.n : (v.full ? v.fl.N : w->Naug);
   v.ldk = pad4(v.N);
   v.sK = (size_t)v.N * v.ldk;
   v.ldq = s.ns; v.ldm = s.ns; v.ldmt = s.ms;
   v.sQ = (size_t)s.n * s.ns; v.sM = (size_t)s.m * s.ns; v.sMT = (size_t)s.n * s.ms;
   v.sp = (size_t)N_NSLOTS * s.ns + (size_t)N_MSLOTS * s.ms;
-  v.ssol = pad4(w->Naug);
+  v.ssol = pad4(std::max(w->Naug, v.N));
   v.tol = opt.tolerance; v.ftb = opt.fraction_to_boundary; v.sigma_pow = opt.sigma_power;
   v.max_iter = opt.max_iter;
   w->refine = v.normal ? (opt.refine_steps < 0 ? 1 : opt.refine_steps) : 0;
@@ -301,6 +304,10 @@ static void iteration_matvecs(Workspace& w, const View& v, int nslots) {
 
 static void assemble_and_factor(Workspace& w, const View& v, int nslots) {
   const Shape& s = v.s;
+  if (v.full) {
+    launch_assemble_full(w.st, v, nslots);
+    return;
+  }
   launch_assemble(w.st, v, nslots);
   if (v.normal && s.m > 0) {
     launch_scale_cols(w.st, nslots, v.active, v.MT, w.MTW, v.ldmt, v.sMT, s.n, s.m, v.W, s.ms);
@@ -327,6 +334,13 @@ static void condensed_solve(Workspace& w, const View& v, int nslots, const doubl
 // one Newton solve with the current factor: rhs -> direction (mode 0: affine, 1: corrector)
 static void newton_direction(Workspace& w, const View& v, int nslots, int mode) {
   const Shape& s = v.s;
+  if (v.full) {  // every Delta comes out of the one solve: no back-substitution
+    const FactorPlan fp = plan_of(w, nslots, v.active);
+    launch_full_rhs(w.st, v, nslots);
+    launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
+    launch_full_unpack(w.st, v, nslots, mode);
+    return;
+  }
   if (!v.normal) {
     const FactorPlan fp = plan_of(w, nslots, v.active);
     launch_prepare_sol(w.st, v, nslots, v.rhs, 0);

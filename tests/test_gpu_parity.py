@@ -124,6 +124,29 @@ def test_assemble_matches_oracle(z, name, reduction):
     s.close()
 
 
+@pytest.mark.parametrize("name", [k for k in sorted(CASES) if CASES[k]().n <= 64])
+@pytest.mark.parametrize("k", [0, 3])
+def test_assemble_full_matches_model(z, name, k):
+    """FULL reduction: the CUDA assembly of the symmetrised un-reduced Newton system equals the numpy model
+    (tests/full_model.py, itself checked against the oracle's step on the CPU) entry by entry."""
+    import full_model as fm
+    p = CASES[name]()
+    it = np.zeros(p.iterate_len)
+    if k:
+        it = ol.port_solve(p, cap_iters=k, stop_after_cap=True).iterate.copy()
+    else:
+        ol.port().orc_initial_iterate(p.c_struct(), ol._ptr(it))
+    K, _, L = fm.full_system(p, it)
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=z.FULL))
+    s.set_iterate(it)
+    Kg = s.assemble()
+    s.close()
+    assert Kg.shape == K.shape == (L["N"], L["N"])
+    assert np.array_equal(Kg != 0.0, K != 0.0), "sparsity pattern"
+    assert relerr(Kg, K) < 1e-15
+    assert np.array_equal(Kg, Kg.T)
+
+
 def _step_parity(z, p, iterate, reduction, tol=STEP_TOL):
     tr = ol.port_solve(p, cap_iters=1, stop_after_cap=True, iterate=iterate)
     s = z.Solver(z.Problem.from_data(p), z.Options(reduction=reduction))
@@ -139,13 +162,13 @@ def _step_parity(z, p, iterate, reduction, tol=STEP_TOL):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("reduction", [0, 1, 2])
 def test_newton_step_at_initial_point(z, name, reduction):
     _step_parity(z, CASES[name](), None, reduction)
 
 
 @pytest.mark.parametrize("name", ["ineq_box_64x32", "eq_box_40x20", "cfg1_eq_box_200x100", "cfg4_unit_256x128"])
-@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("reduction", [0, 1, 2])
 @pytest.mark.parametrize("k", [2, 4])
 def test_newton_step_at_reference_iterate(z, name, reduction, k):
     """Feed the CUDA path the oracle's iterate after k iterations, compare that iteration's steps."""
@@ -155,7 +178,7 @@ def test_newton_step_at_reference_iterate(z, name, reduction, k):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("reduction", [0, 1, 2])
 def test_full_solve_matches_reference_golden(z, name, reduction):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     p = CASES[name]()
@@ -185,7 +208,7 @@ def test_warm_start_second_solve_is_immediate(z):
     s.close()
 
 
-@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("reduction", [0, 1, 2])
 def test_batch_matches_oracle_per_problem(z, reduction):
     count, n, m = 12, 48, 20
     probs = [P.ineq_box(n, m, 2000 + i, kind="shift") for i in range(count)]
