@@ -17,6 +17,8 @@
  *   stdout "iter:" / "b:" lines Optimizer.cpp:131-132, :359           ipmz_result + ipmz_get_trace
  *   LinearSolvers::ldlt_decomposition     LinearSolvers.h:11          ipmz_ldlt_decomposition
  *   LinearSolvers::overwriting_solve_ldlt LinearSolvers.h:16-17       ipmz_overwriting_solve_ldlt
+ *   LinearSolvers::symmetric_indefinite_factorization  LinearSolvers.h:24-25  ipmz_symmetric_indefinite_factorization
+ *   LinearSolvers::overwriting_solve_bunch_kaufman     LinearSolvers.h:29-31  ipmz_overwriting_solve_bunch_kaufman
  *   (batched independent QPs: no reference counterpart, north_star)   ipmz_batch_*
  *
  * Conventions: every entry point returns 0 on success and a non-zero ipmz_status otherwise;
@@ -144,6 +146,13 @@ int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out);
  * replaced by 1e-8 (LinearSolvers.cpp:28). */
 int ipmz_ldlt_decomposition(int n, const double* A, double* L, double* D);
 int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double* b);
+
+/* Bunch-Kaufman (LinearSolvers.cpp:76-318).  LD: n x n copy of A whose lower triangle holds L and the 1x1 / 2x2
+ * blocks of D (upper triangle = A's, as in the reference); ipiv[k] >= 0: 1x1 pivot interchanged with row ipiv[k];
+ * ipiv[k] = ipiv[k+1] = -kp: 2x2 pivot whose second row was interchanged with row kp.  The factorization is
+ * bit-exact against the reference (same pivots, same bits); the solve agrees to rounding. */
+int ipmz_symmetric_indefinite_factorization(int n, const double* A, double* LD, int* ipiv);
+int ipmz_overwriting_solve_bunch_kaufman(int n, const double* LD, const int* ipiv, double* b);
 
 /* ---- device-resident factor + solve (bench / roofline path) ---- */
 int ipmz_factor_create(int n, int device, ipmz_factor_handle* out);

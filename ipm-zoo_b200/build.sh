@@ -5,7 +5,7 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="${EXTRA_NVCC_FLAGS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++"
 mkdir -p "$HERE/csrc/_obj"
-for f in vector_kernels assemble full_system factor dataflow dataflow_tma trsv solver linear_solvers; do
+for f in vector_kernels assemble full_system bunch_kaufman factor dataflow dataflow_tma trsv solver linear_solvers; do
   if [ ! -f "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/$f.cu" -nt "$HERE/csrc/_obj/$f.o" ] || \
      [ "$HERE/csrc/ipmz_device.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ldlt_device.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || \
      [ "$HERE/csrc/ldlt_schedule.hpp" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/dataflow_kernel.cuh" -nt "$HERE/csrc/_obj/$f.o" ] || [ "$HERE/csrc/ipmz_kernels.h" -nt "$HERE/csrc/_obj/$f.o" ] || \

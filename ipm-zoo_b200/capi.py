@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_create", "ipmz_destroy", "ipmz_set_iterate", "ipmz_get_iterate", "ipmz_reset_iterate",
     "ipmz_solve", "ipmz_newton_step", "ipmz_get_trace", "ipmz_assemble",
     "ipmz_ldlt_decomposition", "ipmz_overwriting_solve_ldlt",
+    "ipmz_symmetric_indefinite_factorization", "ipmz_overwriting_solve_bunch_kaufman",
     "ipmz_factor_create", "ipmz_factor_destroy", "ipmz_factor_set_matrix", "ipmz_factor_set_rhs",
     "ipmz_factor_run", "ipmz_factor_profile", "ipmz_factor_get_solution", "ipmz_factor_get_ld",
     "ipmz_factor_info", "ipmz_schedule_check",
@@ -94,6 +95,8 @@ def lib():
         L.ipmz_assemble.argtypes = [vp, dp, C.POINTER(C.c_int)]
         L.ipmz_ldlt_decomposition.argtypes = [C.c_int, dp, dp, dp]
         L.ipmz_overwriting_solve_ldlt.argtypes = [C.c_int, dp, dp, dp]
+        L.ipmz_symmetric_indefinite_factorization.argtypes = [C.c_int, dp, dp, C.POINTER(C.c_int)]
+        L.ipmz_overwriting_solve_bunch_kaufman.argtypes = [C.c_int, dp, C.POINTER(C.c_int), dp]
         L.ipmz_factor_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
         L.ipmz_factor_destroy.argtypes = [vp]
         L.ipmz_factor_set_matrix.argtypes = [vp, dp]
@@ -404,6 +407,26 @@ def ldlt_decomposition(A):
     L, D = np.zeros((n, n)), np.zeros(n)
     _check(lib().ipmz_ldlt_decomposition(n, _ptr(A), _ptr(L), _ptr(D)))
     return L, D
+
+
+def symmetric_indefinite_factorization(A):
+    """LinearSolvers::symmetric_indefinite_factorization (LinearSolvers.h:24-25): returns (LD, ipiv)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    LD = np.zeros((n, n))
+    ipiv = np.zeros(n, dtype=np.int32)
+    _check(lib().ipmz_symmetric_indefinite_factorization(n, _ptr(A), _ptr(LD), ipiv.ctypes.data_as(C.POINTER(C.c_int))))
+    return LD, ipiv
+
+
+def overwriting_solve_bunch_kaufman(LD, ipiv, b):
+    """LinearSolvers::overwriting_solve_bunch_kaufman (LinearSolvers.h:29-31): b is overwritten."""
+    LD = np.ascontiguousarray(LD, dtype=np.float64)
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    assert b.dtype == np.float64 and b.flags.c_contiguous
+    _check(lib().ipmz_overwriting_solve_bunch_kaufman(LD.shape[0], _ptr(LD), ipiv.ctypes.data_as(C.POINTER(C.c_int)),
+                                                     _ptr(b)))
+    return b
 
 
 def overwriting_solve_ldlt(L, D, b):

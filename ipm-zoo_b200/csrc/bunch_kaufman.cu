@@ -1,0 +1,437 @@
+// ipm-zoo_b200/csrc/bunch_kaufman.cu -- symmetric indefinite factorization with Bunch-Kaufman pivoting and
+// its solve, on the device.
+//
+// Reference: LinearSolvers::symmetric_indefinite_factorization (LinearSolvers.cpp:76-207) and
+// overwriting_solve_bunch_kaufman (:209-318): the unblocked LAPACK dsytf2 'L' scheme, alpha = (1+sqrt 17)/8,
+// ipiv[k] >= 0 = 1x1 pivot interchanged with row ipiv[k], a negative pair = 2x2 pivot whose second row was
+// interchanged with row -ipiv[k].  The reference never reaches it from Optimizer::solve (solve_indefinite_ is
+// ASSERT(false), Optimizer.cpp:75); it is part of the public LinearSolvers header, and here it also carries the
+// EqualityHandling::None (indefinite KKT) path of the solver.
+//
+// The factorization is BIT-EXACT against the reference, pivots included: pivot search and interchanges are
+// index work, and every trailing element receives the reference's own sequence of individually rounded
+// operations (a -= (rp * a_jk) * a_ik: a multiply, a multiply and a subtract, never fused -- the reference is
+// compiled without FMA contraction for x86-64), so the algorithm can be laid out for the GPU freely as long as
+// each element sees its updates in pivot order:
+//   * the trailing matrix is kept FULLY symmetric in a scratch copy (element (a,b) and (b,a) are computed with
+//     the same operands in the same order, so they stay bitwise equal); column k of the lower triangle is then
+//     row k of the upper one and the pivot searches (column k, row/column imax) and the pivot column of the
+//     rank-1 / rank-2 update are contiguous, coalesced row reads;
+//   * rows are dealt cyclically to the CTAs of a team; one warp updates one row per trip, lanes along the row;
+//   * three team barriers per pivot step (search -> interchange -> update); a single large matrix uses all
+//     SMs (cooperative launch, grid barrier), a batch uses one CTA per matrix (__syncthreads);
+//   * the finished column of L is mirrored into the dead upper row so that the solves read rows, not columns.
+// HBM/L2-bound: the update reads and writes (n-k)^2 doubles per pivot (2 x the lower triangle), i.e.
+// (2/3) n^3 * 8 B of traffic against L2 when the matrix fits (n <= ~3900 in 126 MB), HBM beyond.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/ipmz.h"
+#include "ipmz_device.cuh"
+#include "ipmz_kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace ipmz {
+int ipmz_fail(int code, const std::string& msg);
+int ipmz_ensure_device(int device);
+
+namespace {
+
+constexpr int BK_TPB = 512;
+constexpr int BK_WARPS = BK_TPB / 32;
+
+struct BkArgs {
+  double* S;      // [count][n x ld] in: matrix (lower triangle significant); out: L / D below, L^T mirror above
+  int ld;
+  size_t sS;
+  int n;
+  int* ipiv;      // [count][sP]
+  size_t sP;
+  const int* active;
+  double alpha;
+  int mirror_input;  // 1: copy the lower triangle over the upper one first (input not known symmetric)
+};
+
+template <bool TEAM>
+__device__ __forceinline__ void team_sync() {
+  if (TEAM) cg::this_grid().sync();
+  else __syncthreads();
+}
+
+// max |row[j]| over j in [j0, j1) except j == skip, and the FIRST index attaining it (the reference's
+// strict `v > max` scan, LinearSolvers.cpp:86-101); NaNs never win, as in the reference.
+__device__ void block_absmax(const double* __restrict__ row, int j0, int j1, int skip, double* out_val, int* out_arg,
+                             double* sh_val, int* sh_arg) {
+  double v = 0.0;
+  int arg = 0x7fffffff;
+  for (int j = j0 + (int)threadIdx.x; j < j1; j += BK_TPB) {
+    if (j == skip) continue;
+    const double t = fabs(row[j]);
+    if (t > v) { v = t; arg = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ov > v || (ov == v && oa < arg)) { v = ov; arg = oa; }
+  }
+  __syncthreads();  // previous use of the scratch is over
+  if ((threadIdx.x & 31) == 0) { sh_val[threadIdx.x >> 5] = v; sh_arg[threadIdx.x >> 5] = arg; }
+  __syncthreads();
+  v = sh_val[0]; arg = sh_arg[0];
+#pragma unroll
+  for (int w = 1; w < BK_WARPS; ++w) {
+    const double ov = sh_val[w];
+    const int oa = sh_arg[w];
+    if (ov > v || (ov == v && oa < arg)) { v = ov; arg = oa; }
+  }
+  *out_val = v;
+  *out_arg = (v == 0.0) ? 0 : arg;
+}
+
+template <bool TEAM>
+__global__ void __launch_bounds__(BK_TPB) k_bk_factor(BkArgs a) {
+  __shared__ double sh_val[BK_WARPS];
+  __shared__ int sh_arg[BK_WARPS];
+  const int p = a.active ? a.active[blockIdx.y] : (int)blockIdx.y;
+  double* __restrict__ S = a.S + (size_t)p * a.sS;
+  int* __restrict__ ipiv = a.ipiv + (size_t)p * a.sP;
+  const int n = a.n, ld = a.ld;
+  const int team = gridDim.x, blk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto E = [&](int r, int c) -> double& { return S[(size_t)r * ld + c]; };
+  // first row >= r owned by this CTA
+  auto first_owned = [&](int r) { const int q = (r - blk + team - 1) / team; return blk + (q < 0 ? 0 : q) * team; };
+
+  if (a.mirror_input) {
+    for (int r = first_owned(0) + warp * team; r < n; r += BK_WARPS * team)
+      for (int c = lane; c < r; c += 32) E(c, r) = E(r, c);
+    team_sync<TEAM>();
+  }
+
+  int k = 0;
+  int pk = -1, pw = 0;  // previous step: first column and width of the L columns still to be mirrored
+  while (k < n) {
+    // ---- pivot search: every CTA evaluates it on the same (stable) data ----
+    int width = 1, kp = k, imax;
+    bool nothing = false;
+    double colmax;
+    const double akk = fabs(E(k, k));
+    block_absmax(S + (size_t)k * ld, k + 1, n, -1, &colmax, &imax, sh_val, sh_arg);
+    if (akk == 0.0 && colmax == 0.0) {
+      nothing = true;  // column k is zero (LinearSolvers.cpp:111-117)
+    } else if (!(akk >= __dmul_rn(a.alpha, colmax))) {
+      double rowmax;
+      int dummy;
+      block_absmax(S + (size_t)imax * ld, k, n, imax, &rowmax, &dummy, sh_val, sh_arg);
+      if (__dmul_rn(akk, rowmax) >= __dmul_rn(__dmul_rn(a.alpha, colmax), colmax)) kp = k;
+      else if (fabs(E(imax, imax)) >= __dmul_rn(a.alpha, rowmax)) kp = imax;
+      else { kp = imax; width = 2; }
+    }
+    const int kk = k + width - 1;
+    team_sync<TEAM>();  // nobody still scans the rows the interchange is about to move
+
+    // ---- mirror the previous pivot's L column(s) into their (now dead) upper rows, and interchange ----
+    if (pk >= 0) {
+      for (int r = first_owned(pk + pw) + tid * team; r < n; r += BK_TPB * team) {
+        E(pk, r) = E(r, pk);
+        if (pw == 2) E(pk + 1, r) = E(r, pk + 1);
+      }
+    }
+    if (!nothing && kp != kk) {
+      // symmetric interchange of rows/columns kk and kp of the trailing block S[k:, k:]
+      for (int r = first_owned(k) + tid * team; r < n; r += BK_TPB * team) {
+        if (r == kk || r == kp) continue;
+        const double t = E(r, kk); E(r, kk) = E(r, kp); E(r, kp) = t;
+      }
+      if (blk == kk % team) {
+        for (int c = k + tid; c < n; c += BK_TPB) {
+          if (c == kp) continue;  // the off-diagonal pair (kk,kp) / (kp,kk) maps onto itself
+          if (c == kk) { const double t = E(kk, kk); E(kk, kk) = E(kp, kp); E(kp, kp) = t; continue; }
+          const double t = E(kk, c); E(kk, c) = E(kp, c); E(kp, c) = t;
+        }
+      }
+    }
+    if (blk == 0 && tid == 0) {
+      if (width == 1) ipiv[k] = kp;
+      else { ipiv[k] = -kp; ipiv[k + 1] = -kp; }
+    }
+    team_sync<TEAM>();
+
+    // ---- trailing update: element (r, c) of S[k+width:, k+width:] with lo = min(r,c), hi = max(r,c) ----
+    if (!nothing) {
+      const double* __restrict__ w0 = S + (size_t)k * ld;  // row k = column k of the lower triangle (unscaled)
+      if (width == 1) {
+        const double rp = __ddiv_rn(1.0, w0[k]);
+        for (int r = first_owned(k + 1) + warp * team; r < n; r += BK_WARPS * team) {
+          double* __restrict__ row = S + (size_t)r * ld;
+          const double wr = w0[r];
+          const double sfr = __dmul_rn(rp, wr);  // = L(r,k)
+          for (int c = k + 1 + lane; c < n; c += 32) {
+            const double wc = w0[c];
+            const double prod = (c <= r) ? __dmul_rn(__dmul_rn(rp, wc), wr) : __dmul_rn(sfr, wc);
+            row[c] = __dsub_rn(row[c], prod);
+          }
+          if (lane == 0) row[k] = sfr;
+        }
+      } else {
+        const double* __restrict__ w1 = S + (size_t)(k + 1) * ld;
+        double d21 = w1[k];
+        const double d11 = __ddiv_rn(w1[k + 1], d21);
+        const double d22 = __ddiv_rn(w0[k], d21);
+        const double t = __ddiv_rn(1.0, __dsub_rn(__dmul_rn(d11, d22), 1.0));
+        d21 = __ddiv_rn(t, d21);
+        for (int r = first_owned(k + 2) + warp * team; r < n; r += BK_WARPS * team) {
+          double* __restrict__ row = S + (size_t)r * ld;
+          const double e0r = w0[r], e1r = w1[r];
+          const double wkr = __dmul_rn(d21, __dsub_rn(__dmul_rn(d11, e0r), e1r));
+          const double wk1r = __dmul_rn(d21, __dsub_rn(__dmul_rn(d22, e1r), e0r));
+          for (int c = k + 2 + lane; c < n; c += 32) {
+            const double e0c = w0[c], e1c = w1[c];
+            double prod;
+            if (c <= r) {  // lo = c: A[r][c] -= A[r][k] * wk(c) + A[r][k+1] * wk1(c)
+              const double wkc = __dmul_rn(d21, __dsub_rn(__dmul_rn(d11, e0c), e1c));
+              const double wk1c = __dmul_rn(d21, __dsub_rn(__dmul_rn(d22, e1c), e0c));
+              prod = __dadd_rn(__dmul_rn(e0r, wkc), __dmul_rn(e1r, wk1c));
+            } else {       // mirror of A[c][r]: A[c][k] * wk(r) + A[c][k+1] * wk1(r)
+              prod = __dadd_rn(__dmul_rn(e0c, wkr), __dmul_rn(e1c, wk1r));
+            }
+            row[c] = __dsub_rn(row[c], prod);
+          }
+          if (lane == 0) { row[k] = wkr; row[k + 1] = wk1r; }
+        }
+      }
+      pk = k; pw = width;
+    } else {
+      pk = -1;
+    }
+    team_sync<TEAM>();
+    k += width;
+  }
+  // mirror of the last pivot is empty (no rows below it) unless it was skipped earlier: nothing left to do
+}
+
+// x <- solution of (L D L^T with interchanges) x = b, LinearSolvers.cpp:209-318.  One CTA per system, x in shared
+// memory; S holds L / D below the diagonal and L^T above it, so each pivot step reads one contiguous row.
+// Parallel sums: agrees with the reference's sequential solve to rounding, not bitwise.
+__global__ void __launch_bounds__(BK_TPB) k_bk_solve(BkArgs a, double* __restrict__ xall, size_t sx) {
+  extern __shared__ double xs[];
+  __shared__ double red[BK_WARPS];
+  const int p = a.active ? a.active[blockIdx.y] : (int)blockIdx.y;
+  const double* __restrict__ S = a.S + (size_t)p * a.sS;
+  const int* __restrict__ ipiv = a.ipiv + (size_t)p * a.sP;
+  double* __restrict__ x = xall + (size_t)p * sx;
+  const int n = a.n, ld = a.ld, tid = threadIdx.x;
+  for (int i = tid; i < n; i += BK_TPB) xs[i] = x[i];
+  __syncthreads();
+  int k = 0;
+  while (k < n) {
+    const double* __restrict__ r0 = S + (size_t)k * ld;
+    if (ipiv[k] >= 0) {
+      const int kp = ipiv[k];
+      const double bk = xs[kp];  // value of b[k] after the interchange
+      __syncthreads();
+      if (tid == 0) { xs[kp] = xs[k]; xs[k] = bk / r0[k]; }
+      const double mlt = -bk;
+      __syncthreads();
+      for (int i = k + 1 + tid; i < n; i += BK_TPB) xs[i] += r0[i] * mlt;
+      k += 1;
+    } else {
+      const int kp = -ipiv[k];
+      const double* __restrict__ r1 = S + (size_t)(k + 1) * ld;
+      const double b0v = xs[k], b1v = xs[kp];
+      __syncthreads();
+      if (tid == 0) {
+        xs[kp] = xs[k + 1];
+        const double off = r1[k];
+        const double a0 = r0[k] / off, a1 = r1[k + 1] / off;
+        const double den = a0 * a1 - 1.0;
+        const double c0 = b0v / off, c1 = b1v / off;
+        xs[k] = (a1 * c0 - c1) / den;
+        xs[k + 1] = (a0 * c1 - c0) / den;
+      }
+      const double m0 = -b0v, m1 = -b1v;
+      __syncthreads();
+      for (int i = k + 2 + tid; i < n; i += BK_TPB) xs[i] += r0[i] * m0 + r1[i] * m1;
+      k += 2;
+    }
+    __syncthreads();
+  }
+  auto block_sum = [&](double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < BK_WARPS; ++w) s += red[w];
+    return s;
+  };
+  k = n - 1;
+  while (k >= 0) {
+    if (ipiv[k] >= 0) {
+      const double* __restrict__ r0 = S + (size_t)k * ld;
+      double s = 0.0;
+      for (int i = k + 1 + tid; i < n; i += BK_TPB) s += r0[i] * xs[i];
+      s = block_sum(s);
+      const int kp = ipiv[k];
+      if (tid == 0) {
+        const double v = xs[k] - s;
+        xs[k] = xs[kp]; xs[kp] = v;  // kp == k: plain store of v
+        if (kp == k) xs[k] = v;
+      }
+      k -= 1;
+    } else {
+      const double* __restrict__ r1 = S + (size_t)k * ld;        // column k
+      const double* __restrict__ r0 = S + (size_t)(k - 1) * ld;  // column k-1
+      double s1 = 0.0, s0 = 0.0;
+      for (int i = k + 1 + tid; i < n; i += BK_TPB) { s1 += r1[i] * xs[i]; s0 += r0[i] * xs[i]; }
+      s1 = block_sum(s1);
+      s0 = block_sum(s0);
+      const int kp = -ipiv[k];
+      if (tid == 0) {
+        xs[k - 1] -= s0;
+        const double v = xs[k] - s1;
+        xs[k] = xs[kp]; xs[kp] = v;
+        if (kp == k) xs[k] = v;
+      }
+      k -= 2;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += BK_TPB) x[i] = xs[i];
+}
+
+// lower triangle (strictly below the diagonal) -> upper triangle, for factors that arrive from the host
+__global__ void k_bk_mirror(double* __restrict__ S, int ld, int n) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  for (int c = threadIdx.x & 31; c < r; c += 32) S[(size_t)c * ld + r] = S[(size_t)r * ld + c];
+}
+
+int g_bk_sms = 0;
+bool g_bk_init = false;
+
+}  // namespace
+
+double bk_alpha() { return (1.0 + std::sqrt(17.0)) / 8.0; }
+
+// Factor `nslots` matrices in place.  One matrix: all SMs as one team (cooperative launch) when it is large
+// enough to feed them; a batch: one CTA per matrix.  Returns a cudaError_t.
+int launch_bk_factor(cudaStream_t st, int nslots, const int* active, double* S, int ld, size_t sS, int n, int* ipiv,
+                     size_t sP, int mirror_input) {
+  if (n <= 0 || nslots <= 0) return 0;
+  if (!g_bk_init) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_bk_sms, cudaDevAttrMultiProcessorCount, dev);
+    g_bk_init = true;
+  }
+  BkArgs a{S, ld, sS, n, ipiv, sP, active, bk_alpha(), mirror_input};
+  int team = 1;
+  if (nslots == 1 && n >= 256) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bk_factor<true>, BK_TPB, 0);
+    team = g_bk_sms * (per_sm > 0 ? 1 : 0);
+    const int want = (n + BK_WARPS - 1) / BK_WARPS;  // at least one row per warp in the first steps
+    if (team > want) team = want;
+    if (team < 1) team = 1;
+  }
+  count_launch();
+  if (team > 1) {
+    void* args[] = {&a};
+    return (int)cudaLaunchCooperativeKernel((void*)k_bk_factor<true>, dim3(team, 1), dim3(BK_TPB), args, 0, st);
+  }
+  k_bk_factor<false><<<dim3(1, nslots), BK_TPB, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double* S, int ld, size_t sS, int n,
+                    const int* ipiv, size_t sP, double* x, size_t sx) {
+  if (n <= 0 || nslots <= 0) return 0;
+  BkArgs a{const_cast<double*>(S), ld, sS, n, const_cast<int*>(ipiv), sP, active, 0.0, 0};
+  const size_t smem = sizeof(double) * (size_t)n;
+  static size_t opted = 0;
+  if (smem > 48 * 1024 && smem > opted) {
+    const cudaError_t e = cudaFuncSetAttribute(k_bk_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    opted = smem;
+  }
+  k_bk_solve<<<dim3(1, nslots), BK_TPB, smem, st>>>(a, x, sx);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ipmz
+
+using namespace ipmz;
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return ipmz_fail(IPMZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" {
+
+int ipmz_symmetric_indefinite_factorization(int n, const double* A, double* LD, int* ipiv) {
+  if (n < 0 || (n > 0 && (!A || !LD || !ipiv))) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  if (n == 0) return IPMZ_OK;
+  int rc;
+  if ((rc = ipmz_ensure_device(0))) return rc;
+  const int ld = pad4(n);
+  DevBuf S, P;
+  CUDA_TRY(cudaMalloc(&S.p, sizeof(double) * (size_t)n * ld));
+  CUDA_TRY(cudaMalloc(&P.p, sizeof(int) * (size_t)n));
+  CUDA_TRY(cudaMemset(S.p, 0, sizeof(double) * (size_t)n * ld));
+  CUDA_TRY(cudaMemcpy2D(S.p, sizeof(double) * ld, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+  CUDA_TRY((cudaError_t)launch_bk_factor(nullptr, 1, nullptr, (double*)S.p, ld, (size_t)n * ld, n, (int*)P.p, (size_t)n, 1));
+  CUDA_TRY(cudaDeviceSynchronize());
+  // the reference returns a copy of the input whose lower triangle was overwritten: keep the caller's upper triangle
+  std::vector<double> tmp((size_t)n * n);
+  CUDA_TRY(cudaMemcpy2D(tmp.data(), sizeof(double) * n, S.p, sizeof(double) * ld, sizeof(double) * n, n,
+                        cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(ipiv, P.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) LD[(size_t)i * n + j] = (j <= i) ? tmp[(size_t)i * n + j] : A[(size_t)i * n + j];
+  return IPMZ_OK;
+}
+
+int ipmz_overwriting_solve_bunch_kaufman(int n, const double* LD, const int* ipiv, double* b) {
+  if (n < 0 || (n > 0 && (!LD || !ipiv || !b))) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  if (n == 0) return IPMZ_OK;
+  if ((size_t)n * sizeof(double) > 200 * 1024) return ipmz_fail(IPMZ_ERR_ARG, "n too large for the one-CTA Bunch-Kaufman solve");
+  int rc;
+  if ((rc = ipmz_ensure_device(0))) return rc;
+  const int ld = pad4(n);
+  DevBuf S, P, X;
+  CUDA_TRY(cudaMalloc(&S.p, sizeof(double) * (size_t)n * ld));
+  CUDA_TRY(cudaMalloc(&P.p, sizeof(int) * (size_t)n));
+  CUDA_TRY(cudaMalloc(&X.p, sizeof(double) * (size_t)ld));
+  CUDA_TRY(cudaMemcpy2D(S.p, sizeof(double) * ld, LD, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(P.p, ipiv, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(X.p, b, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  k_bk_mirror<<<(n + 7) / 8, 256>>>((double*)S.p, ld, n);
+  count_launch();
+  CUDA_TRY((cudaError_t)launch_bk_solve(nullptr, 1, nullptr, (const double*)S.p, ld, (size_t)n * ld, n, (const int*)P.p,
+                                        (size_t)n, (double*)X.p, (size_t)ld));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(b, X.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return IPMZ_OK;
+}
+
+}  // extern "C"

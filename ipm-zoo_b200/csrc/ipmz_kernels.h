@@ -41,6 +41,14 @@ void launch_assemble_full(cudaStream_t st, const View& v, int nslots);
 void launch_full_rhs(cudaStream_t st, const View& v, int nslots);             // R, V -> sol
 void launch_full_unpack(cudaStream_t st, const View& v, int nslots, int mode);  // sol -> DA / D, step length
 
+// ---- bunch_kaufman.cu: symmetric indefinite factorization (LinearSolvers.cpp:76-318), bit-exact pivots ----
+// S: in = matrix (lower triangle significant), out = L / D on and below the diagonal, L^T mirrored above it.
+// Both return a cudaError_t.
+int launch_bk_factor(cudaStream_t st, int nslots, const int* active, double* S, int ld, size_t sS, int n, int* ipiv,
+                     size_t sP, int mirror_input);
+int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double* S, int ld, size_t sS, int n,
+                    const int* ipiv, size_t sP, double* x, size_t sx);
+
 // ---- factor.cu ----
 // Side stream + events of the look-ahead schedule of launch_ldlt (one per handle).
 struct LookAhead {
