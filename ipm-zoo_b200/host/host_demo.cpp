@@ -31,6 +31,11 @@ int main() {
     std::vector<double> b = {2.0, 1.0};
     LinearSolvers::overwriting_solve_ldlt(L, D, b);
     std::cout << "ldlt: L10=" << L[1][0] << " D=" << D[0] << "," << D[1] << " x=" << b[0] << "," << b[1] << std::endl;
+    // Bunch-Kaufman mirror: a zero diagonal forces a 2x2 pivot
+    auto [F, piv] = LinearSolvers::symmetric_indefinite_factorization({{0.0, 1.0}, {1.0, 0.0}});
+    std::vector<double> b2 = {3.0, 5.0};
+    LinearSolvers::overwriting_solve_bunch_kaufman(F, piv, b2);
+    std::cout << "bunch-kaufman: ipiv=" << piv[0] << "," << piv[1] << " x=" << b2[0] << "," << b2[1] << std::endl;
     // error convention: l >= u asserts
     try {
       Data bad = data;

@@ -149,6 +149,25 @@ void overwriting_solve_ldlt(const Matrix& L, const std::vector<double>& D, std::
   const auto flat = flatten(L, n);
   check(ipmz_overwriting_solve_ldlt(n, flat.data(), D.data(), b.data()));
 }
+
+std::pair<Matrix, std::vector<int>> symmetric_indefinite_factorization(const Matrix& A) {
+  const int n = (int)A.size();
+  const auto flat = flatten(A, n);  // non-square throws like the reference's ASSERT (LinearSolvers.cpp:80-81)
+  std::vector<double> LD((size_t)n * n);
+  std::vector<int> ipiv(n, 0);
+  check(ipmz_symmetric_indefinite_factorization(n, flat.data(), LD.data(), ipiv.data()));
+  Matrix out(n, std::vector<double>(n));
+  for (int i = 0; i < n; ++i) std::memcpy(out[i].data(), LD.data() + (size_t)i * n, sizeof(double) * n);
+  return {out, ipiv};
+}
+
+void overwriting_solve_bunch_kaufman(const Matrix& L, const std::vector<int>& ipiv, std::vector<double>& b) {
+  const int n = (int)b.size();
+  if ((int)ipiv.size() != n || (int)L.size() != n) throw AssertionError("Assertion failed: ipiv.size() == n && L.size() == n");
+  if (n == 0) return;
+  const auto flat = flatten(L, n);
+  check(ipmz_overwriting_solve_bunch_kaufman(n, flat.data(), ipiv.data(), b.data()));
+}
 }  // namespace LinearSolvers
 
 }  // namespace NumericalOptimization

@@ -4,7 +4,7 @@
 // C ABI (include/ipmz.h).  Same names, argument meaning and error behaviour as
 //   NumericalOptimization::Data / build_environment   include/NumericalOptimization/EnvironmentBuilder.h:7-20
 //   NumericalOptimization::Optimizer                  include/NumericalOptimization/Optimizer.h:13-20
-//   NumericalOptimization::LinearSolvers::*           include/NumericalOptimization/LinearSolvers.h:11-17
+//   NumericalOptimization::LinearSolvers::*           include/NumericalOptimization/LinearSolvers.h:11-31
 //   SymbolicOptimization::Settings / Bounds           include/SymbolicOptimization.h:28-64
 // but without the symbolic Expression layer: the Environment is a plain map from the
 // reference's variable names ("x", "\\lambda_{A}", "s", "g", ...; SymbolicOptimization.h:5-26,
@@ -95,6 +95,9 @@ class Optimizer {
 namespace LinearSolvers {
 std::pair<Matrix, std::vector<double>> ldlt_decomposition(const Matrix& A);
 void overwriting_solve_ldlt(const Matrix& L, const std::vector<double>& D, std::vector<double>& b);
+// Bunch-Kaufman, LinearSolvers.h:24-31: {factor (lower triangle = L and D blocks, upper = A's), LAPACK-style ipiv}
+std::pair<Matrix, std::vector<int>> symmetric_indefinite_factorization(const Matrix& A);
+void overwriting_solve_bunch_kaufman(const Matrix& L, const std::vector<int>& ipiv, std::vector<double>& b);
 }  // namespace LinearSolvers
 
 }  // namespace NumericalOptimization
