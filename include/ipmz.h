@@ -54,6 +54,17 @@ typedef enum {
 
 enum { IPMZ_BOUNDS_NONE = 0, IPMZ_BOUNDS_LOWER = 1, IPMZ_BOUNDS_UPPER = 2, IPMZ_BOUNDS_BOTH = 3 };
 
+/* ipmz_problem.equalities: Settings::equalities + Settings::equality_handling (SymbolicOptimization.h:42-64). */
+enum {
+  IPMZ_EQ_OFF = 0,            /* Settings::equalities == false */
+  IPMZ_EQ_SLACKED_SLACKS = 1, /* EqualityHandling::SlackedSlacks: C x - t = 0, t - v = d, t + w = d (quasi-definite) */
+  IPMZ_EQ_NONE = 2            /* EqualityHandling::None: C x = d with multiplier lambda_C only
+                                 (SymbolicOptimization.cpp:137-140).  The augmented system gets a zero diagonal
+                                 block, which the reference routes to solve_indefinite_() == ASSERT(false)
+                                 (Optimizer.cpp:63-75); here it is factorized with Bunch-Kaufman pivoting
+                                 (LinearSolvers.cpp:76-318 on the device).  AUGMENTED reduction only. */
+};
+
 /* Which reduction of the Newton system is assembled and factorized (north_star). */
 enum {
   IPMZ_REDUCTION_AUGMENTED = 0, /* quasi-definite [[Hx, M^T],[M, -W^-1]], LDL^T, N = n+m   */
@@ -78,7 +89,7 @@ typedef struct {
   const double* u_x; /* n */
   int ineq_bounds;   /* Settings::inequalities      (IPMZ_BOUNDS_*) */
   int var_bounds;    /* Settings::variable_bounds   (IPMZ_BOUNDS_*) */
-  int equalities;    /* Settings::equalities */
+  int equalities;    /* IPMZ_EQ_* (any non-zero value other than IPMZ_EQ_NONE means SlackedSlacks) */
 } ipmz_problem;
 
 typedef struct {

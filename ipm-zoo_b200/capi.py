@@ -8,6 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 AUGMENTED, NORMAL, FULL = 0, 1, 2
 NONE, LOWER, UPPER, BOTH = 0, 1, 2, 3
+EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE = 0, 1, 2  # ipmz_problem.equalities (EqualityHandling)
 dp = C.POINTER(C.c_double)
 
 EXPORTED_SYMBOLS = [
@@ -180,7 +181,7 @@ class Problem:
         self.m_eq = 0 if self.C is None else self.C.shape[-2]
         self.ineq_bounds = ineq_bounds if self.m_ineq else NONE
         self.var_bounds = var_bounds
-        self.equalities = bool(equalities) and self.m_eq > 0
+        self.equalities = int(equalities) if self.m_eq > 0 else 0
 
     @classmethod
     def from_data(cls, p):

@@ -35,6 +35,7 @@ struct Shape {
   int ilo, iup;      // inequality lower / upper side present (equality rows: both)
   int clamp_x;       // no g/h slacks in the system -> x also clamped to [l_x, u_x] (Optimizer.cpp:296)
   int ncomp;         // number of complementarity entries (denominator of mu)
+  int hard_eq;       // EqualityHandling::None: equality rows carry lambda_C only (no t, v, w) -> indefinite KKT
 };
 
 // FULL reduction (un-reduced Newton system, SymbolicOptimization.cpp:417-433): unknowns in the order

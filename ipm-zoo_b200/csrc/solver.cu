@@ -83,6 +83,7 @@ struct Workspace {
   double* inv = nullptr;
   double* wpanel = nullptr;
   double* MTW = nullptr;  // MT diag(W), B operand of the condensed assembly
+  int* ipiv = nullptr;    // [count][ldk] Bunch-Kaufman pivots (EqualityHandling::None: indefinite KKT)
   TrsvWork tw{};
   LookAhead la{};
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
@@ -141,7 +142,8 @@ static void fill_shape(Shape& s, const ipmz_problem* p) {
   s.ilo = ineq && (p->ineq_bounds == IPMZ_BOUNDS_LOWER || p->ineq_bounds == IPMZ_BOUNDS_BOTH);
   s.iup = ineq && (p->ineq_bounds == IPMZ_BOUNDS_UPPER || p->ineq_bounds == IPMZ_BOUNDS_BOTH);
   s.clamp_x = ineq ? 0 : 1;
-  s.ncomp = (s.ilo + s.iup) * s.mi + 2 * (s.m - s.mi) + (s.ylo + s.zup) * s.n;
+  s.hard_eq = (eq && p->equalities == IPMZ_EQ_NONE) ? 1 : 0;
+  s.ncomp = (s.ilo + s.iup) * s.mi + (s.hard_eq ? 0 : 2 * (s.m - s.mi)) + (s.ylo + s.zup) * s.n;
 }
 
 // host [rows x cols] dense (count blocks back to back) -> device pitched rows
@@ -220,6 +222,8 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   // the reference routes that to solve_indefinite_() == ASSERT(false) (Optimizer.cpp:63-75).
   if (p->m_eq > 0 && !p->equalities)
     return fail(IPMZ_ERR_INDEFINITE, "equality rows given but Settings::equalities is off");
+  if (s.hard_eq && opt.reduction != IPMZ_REDUCTION_AUGMENTED)
+    return fail(IPMZ_ERR_ARG, "EqualityHandling::None (indefinite KKT, Bunch-Kaufman) is available in the AUGMENTED reduction only");
   w->Naug = s.n + s.m;
   v.normal = (opt.reduction == IPMZ_REDUCTION_NORMAL) ? 1 : 0;
   v.full = (opt.reduction == IPMZ_REDUCTION_FULL) ? 1 : 0;
@@ -263,6 +267,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (v.normal) ALLOC(w->MTW, C * v.sMT);
   ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
   ALLOC(w->active_dev, C);
+  if (s.hard_eq) ALLOC(w->ipiv, C * v.ldk);
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
@@ -344,7 +349,8 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
   if (!v.normal) {
     const FactorPlan fp = plan_of(w, nslots, v.active);
     launch_prepare_sol(w.st, v, nslots, v.rhs, 0);
-    launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
+    if (s.hard_eq) launch_bk_solve(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, v.sol, v.ssol);
+    else launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
   } else {
     condensed_solve(w, v, nslots, v.rhs, 0);
     for (int r = 0; r < w.refine; ++r) {
@@ -365,7 +371,9 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
 static void newton_iteration(Workspace& w, const View& v, int nslots, bool update, int record_iter) {
   assemble_and_factor(w, v, nslots);
   const FactorPlan fp = plan_of(w, nslots, v.active);
-  launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
+  // indefinite KKT (zero diagonal block): the reference's solve_indefinite_ hook (Optimizer.cpp:75), Bunch-Kaufman
+  if (v.s.hard_eq) launch_bk_factor(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, 0);
+  else launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
   newton_direction(w, v, nslots, 0);
   launch_mu_affine(w.st, v, nslots);
   launch_residuals_rhs(w.st, v, nslots, 1);

@@ -133,7 +133,11 @@ __global__ void k_initial_point(View v) {
     nslot(V, s, LAMY)[i] = 1.0; nslot(V, s, LAMZ)[i] = 1.0;
     nslot(V, s, YS)[i] = 1.0; nslot(V, s, ZS)[i] = 1.0;
   }
-  if (i < s.m) {
+  if (i < s.m && s.hard_eq && i >= s.mi) {  // EqualityHandling::None: only the multiplier exists
+    mslot(V, s, LAM)[i] = 1.0;
+    mslot(V, s, SV)[i] = 0.0; mslot(V, s, LAML)[i] = 0.0; mslot(V, s, LAMU)[i] = 0.0;
+    mslot(V, s, SL)[i] = 0.0; mslot(V, s, SU)[i] = 0.0;
+  } else if (i < s.m) {
     const double mid = 0.5 * (v.lo[(size_t)p * s.ms + i] + v.up[(size_t)p * s.ms + i]);
     mslot(V, s, LAM)[i] = 1.0;
     mslot(V, s, SV)[i] = (i < s.mi) ? mid : 1.0;  // t (equality slack) starts at 1
@@ -223,7 +227,20 @@ __global__ void __launch_bounds__(TPB) k_residuals_rhs(View v) {
     rhs[i] = b;
   }
 
-  if (i < s.m) {
+  if (i < s.m && s.hard_eq && i >= s.mi) {
+    // EqualityHandling::None (SymbolicOptimization.cpp:137-140): r_lambda = C x - d, Newton row C dx = -r_lambda
+    double rlam;
+    if (MODE == 0) {
+      rlam = v.Mx[(size_t)p * s.ms + i] + -v.lo[(size_t)p * s.ms + i];
+      mslot(R, s, LAM)[i] = rlam;
+      acc[2] += rlam * rlam;
+      v.winv[(size_t)p * s.ms + i] = 0.0;  // the zero diagonal block of the indefinite KKT matrix
+      v.W[(size_t)p * s.ms + i] = 0.0;
+    } else {
+      rlam = mslot(R, s, LAM)[i];
+    }
+    rhs[s.ns + i] = -rlam;
+  } else if (i < s.m) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     const double lam = mslot(V, s, LAM)[i], sv = mslot(V, s, SV)[i];
     double rlam, rsv;
@@ -411,7 +428,9 @@ __global__ void __launch_bounds__(TPB) k_backsub_step(View v) {
       if (dx > 0.0) a[0] = fmin(a[0], (v.ux[(size_t)p * s.ns + i] - x) / dx);
     }
   }
-  if (i < s.m) {
+  if (i < s.m && s.hard_eq && i >= s.mi) {
+    mslot(D, s, LAM)[i] = sol[s.n + i];  // the multiplier is free: no ratio test
+  } else if (i < s.m) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     const double dlam = v.normal ? sol[s.ns + i] : sol[s.n + i];
     mslot(D, s, LAM)[i] = dlam;
@@ -468,7 +487,7 @@ __global__ void __launch_bounds__(TPB) k_mu_affine(View v) {
     if (s.ylo) prod(nslot(V, s, YS)[i], nslot(DA, s, YS)[i], nslot(V, s, LAMY)[i], nslot(DA, s, LAMY)[i]);
     if (s.zup) prod(nslot(V, s, ZS)[i], nslot(DA, s, ZS)[i], nslot(V, s, LAMZ)[i], nslot(DA, s, LAMZ)[i]);
   }
-  if (i < s.m) {
+  if (i < s.m && !(s.hard_eq && i >= s.mi)) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     if (lo) prod(mslot(V, s, SL)[i], mslot(DA, s, SL)[i], mslot(V, s, LAML)[i], mslot(DA, s, LAML)[i]);
     if (up) prod(mslot(V, s, SU)[i], mslot(DA, s, SU)[i], mslot(V, s, LAMU)[i], mslot(DA, s, LAMU)[i]);

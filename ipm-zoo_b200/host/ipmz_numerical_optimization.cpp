@@ -65,9 +65,10 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   // the settings family the reference itself can solve numerically
   if (settings.inequality_handling != InequalityHandling::SlackedSlacks)
     throw AssertionError("Assertion failed: only InequalityHandling::SlackedSlacks is supported");
-  if (settings.equalities && settings.equality_handling == EqualityHandling::None)
-    throw AssertionError("Assertion failed at Optimizer.cpp:75 in solve_indefinite_: false");
-  if (settings.equalities && settings.equality_handling != EqualityHandling::SlackedSlacks)
+  // EqualityHandling::None gives the indefinite KKT matrix the reference routes to solve_indefinite_() ==
+  // ASSERT(false) (Optimizer.cpp:63-75); here that hook is implemented with Bunch-Kaufman (AUGMENTED only).
+  const bool hard_eq = settings.equalities && settings.equality_handling == EqualityHandling::None;
+  if (settings.equalities && !hard_eq && settings.equality_handling != EqualityHandling::SlackedSlacks)
     throw AssertionError("Assertion failed: only EqualityHandling::SlackedSlacks is supported");
   n_ = (int)data.Q.size();
   mi_ = settings.inequalities == Bounds::None ? 0 : (int)data.A_ineq.size();
@@ -84,7 +85,7 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   p.l_x = data.l_x.data(); p.u_x = data.u_x.data();
   p.ineq_bounds = mi_ ? bounds_code(settings.inequalities) : IPMZ_BOUNDS_NONE;
   p.var_bounds = bounds_code(settings.variable_bounds);
-  p.equalities = me_ ? 1 : 0;
+  p.equalities = me_ ? (hard_eq ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS) : IPMZ_EQ_OFF;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = (int)reduction;
