@@ -2,8 +2,9 @@
 //
 // What the adapter does, step by step, and the reference code it stands in for:
 //   1. reduction selection exactly as Optimizer::solve (Optimizer.cpp:63-73): derive the
-//      augmented system with the reference's own symbolic layer and route a symbolic-zero
-//      diagonal block to the reference's ASSERT(false) (solve_indefinite_, :75);
+//      augmented system with the reference's own symbolic layer; a symbolic-zero diagonal block
+//      is the indefinite case (solve_indefinite_, :75, ASSERT(false) in the reference): the zero
+//      block of EqualityHandling::None rows goes to the Bunch-Kaufman path, anything else asserts;
 //   2. classify which slack / dual groups the Newton system contains by looking up the
 //      reference's variable handles in newton_system.variables (they are hash-consed, so
 //      pointer equality is identity: ExprFactory.cpp:14-34) -- this replaces the tree-walking
@@ -69,7 +70,10 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   const bool y = has_var(ns, oe_.s_x_l), z = has_var(ns, oe_.s_x_u);
   const bool ineq = has_var(ns, oe_.lambda_A_ineq), eq = has_var(ns, oe_.lambda_A_eq);
   ASSERT(!ineq || has_var(ns, oe_.s_A_ineq), "inequalities must use InequalityHandling::SlackedSlacks");
-  ASSERT(!eq || (v && w && has_var(ns, oe_.s_A_eq)), "equalities must use EqualityHandling::SlackedSlacks");
+  // EqualityHandling::None (SymbolicOptimization.cpp:137-140): the multiplier exists but no equality slack does
+  hard_eq_ = eq && !has_var(ns, oe_.s_A_eq) && !v && !w;
+  ASSERT(!eq || hard_eq_ || (v && w && has_var(ns, oe_.s_A_eq)),
+         "equalities must use EqualityHandling::SlackedSlacks or EqualityHandling::None");
   ASSERT(!has_var(ns, oe_.p_eq), "EqualityHandling::Regularization is not supported");
 
   size_t nq = 0, mi = 0, me = 0;
@@ -92,7 +96,7 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   p.l_x = lx.data(); p.u_x = ux.data();
   p.ineq_bounds = !ineq ? IPMZ_BOUNDS_NONE : (g && h) ? IPMZ_BOUNDS_BOTH : g ? IPMZ_BOUNDS_LOWER : IPMZ_BOUNDS_UPPER;
   p.var_bounds = (y && z) ? IPMZ_BOUNDS_BOTH : y ? IPMZ_BOUNDS_LOWER : z ? IPMZ_BOUNDS_UPPER : IPMZ_BOUNDS_NONE;
-  p.equalities = eq ? 1 : 0;
+  p.equalities = !eq ? IPMZ_EQ_OFF : hard_eq_ ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = static_cast<int>(reduction);
@@ -103,10 +107,13 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
 B200Optimizer::~B200Optimizer() { ipmz_destroy(handle_); }
 
 void B200Optimizer::solve() {
-  // Optimizer.cpp:63-73: a symbolic zero on the diagonal of the augmented system is the
-  // indefinite case, which the reference does not implement.
+  // Optimizer.cpp:63-73: a symbolic zero on the diagonal of the augmented system is the indefinite case.  The
+  // reference's hook for it (solve_indefinite_, :75) is ASSERT(false); the one pattern implemented here is the
+  // zero block of EqualityHandling::None rows, which the library factorizes with Bunch-Kaufman.
   const auto& lhs = augmented_system_.lhs;
-  for (size_t i = 0; i < lhs.size(); ++i) ASSERT(!(lhs.at(i).at(i) == Expression::zero));
+  bool indefinite = false;
+  for (size_t i = 0; i < lhs.size(); ++i) indefinite = indefinite || (lhs.at(i).at(i) == Expression::zero);
+  ASSERT(!indefinite || hard_eq_);
 
   struct Slot { ExprPtr key; int len; };
   const std::vector<Slot> slots = {

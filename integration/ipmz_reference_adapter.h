@@ -19,7 +19,7 @@ namespace NumericalOptimization {
 
 class B200Optimizer {
  public:
-  enum class Reduction { Augmented = 0, Normal = 1 };
+  enum class Reduction { Augmented = 0, Normal = 1, Full = 2 };
 
   B200Optimizer(Evaluation::Environment& env,
                 const SymbolicOptimization::OptimizationExpressions& optimization_expressions,
@@ -42,6 +42,7 @@ class B200Optimizer {
   int n_ = 0, mi_ = 0, me_ = 0;
   int iterations_ = 0;
   bool converged_ = false;
+  bool hard_eq_ = false;  // EqualityHandling::None: lambda_A_eq without s_A_eq -> indefinite KKT, Bunch-Kaufman
 };
 
 }  // namespace NumericalOptimization

@@ -94,8 +94,37 @@ __device__ void block_absmax(const double* __restrict__ row, int j0, int j1, int
   *out_arg = (v == 0.0) ? 0 : arg;
 }
 
+// row[c] -= f(c, w0[c], w1[c]) for c in [c0, n) by one warp: scalar head up to a 16-byte boundary, then two
+// columns per lane as double2 with four trips unrolled (eight independent 16-byte loads in flight per lane: the
+// update is a pure streaming pass and needs the memory-level parallelism), scalar tail.  Every element still gets
+// exactly one unfused subtract of the value f returns.
+template <bool TWO, class F>
+__device__ __forceinline__ void row_update(double* __restrict__ row, const double* __restrict__ w0,
+                                           const double* __restrict__ w1, int c0, int n, int lane, F f) {
+  if (c0 >= n) return;
+  const int cs = (c0 + 1) & ~1;
+  if (cs > c0 && lane == 0) row[c0] = __dsub_rn(row[c0], f(c0, w0[c0], TWO ? w1[c0] : 0.0));
+  if (cs >= n) return;
+  const int npairs = (n - cs) >> 1;
+  double2* __restrict__ r2 = reinterpret_cast<double2*>(row + cs);
+  const double2* __restrict__ a2 = reinterpret_cast<const double2*>(w0 + cs);
+  const double2* __restrict__ b2 = reinterpret_cast<const double2*>(w1 + cs);
+#pragma unroll 4
+  for (int q = lane; q < npairs; q += 32) {
+    double2 v = r2[q];
+    const double2 a = a2[q];
+    const double2 b = TWO ? b2[q] : make_double2(0.0, 0.0);
+    const int c = cs + 2 * q;
+    v.x = __dsub_rn(v.x, f(c, a.x, b.x));
+    v.y = __dsub_rn(v.y, f(c + 1, a.y, b.y));
+    r2[q] = v;
+  }
+  const int ct = cs + 2 * npairs;
+  if (ct < n && lane == 0) row[ct] = __dsub_rn(row[ct], f(ct, w0[ct], TWO ? w1[ct] : 0.0));
+}
+
 template <bool TEAM>
-__global__ void __launch_bounds__(BK_TPB) k_bk_factor(BkArgs a) {
+__global__ void __launch_bounds__(BK_TPB, 1) k_bk_factor(BkArgs a) {
   __shared__ double sh_val[BK_WARPS];
   __shared__ int sh_arg[BK_WARPS];
   const int p = a.active ? a.active[blockIdx.y] : (int)blockIdx.y;
@@ -172,11 +201,10 @@ __global__ void __launch_bounds__(BK_TPB) k_bk_factor(BkArgs a) {
           double* __restrict__ row = S + (size_t)r * ld;
           const double wr = w0[r];
           const double sfr = __dmul_rn(rp, wr);  // = L(r,k)
-          for (int c = k + 1 + lane; c < n; c += 32) {
-            const double wc = w0[c];
-            const double prod = (c <= r) ? __dmul_rn(__dmul_rn(rp, wc), wr) : __dmul_rn(sfr, wc);
-            row[c] = __dsub_rn(row[c], prod);
-          }
+          row_update<false>(row, w0, w0, k + 1, n, lane, [&](int c, double wc, double) {
+            // lower (c <= r): A[r][c] -= (rp * A[c][k]) * A[r][k]; upper: the mirror of A[c][r]
+            return (c <= r) ? __dmul_rn(__dmul_rn(rp, wc), wr) : __dmul_rn(sfr, wc);
+          });
           if (lane == 0) row[k] = sfr;
         }
       } else {
@@ -191,18 +219,15 @@ __global__ void __launch_bounds__(BK_TPB) k_bk_factor(BkArgs a) {
           const double e0r = w0[r], e1r = w1[r];
           const double wkr = __dmul_rn(d21, __dsub_rn(__dmul_rn(d11, e0r), e1r));
           const double wk1r = __dmul_rn(d21, __dsub_rn(__dmul_rn(d22, e1r), e0r));
-          for (int c = k + 2 + lane; c < n; c += 32) {
-            const double e0c = w0[c], e1c = w1[c];
-            double prod;
+          row_update<true>(row, w0, w1, k + 2, n, lane, [&](int c, double e0c, double e1c) {
             if (c <= r) {  // lo = c: A[r][c] -= A[r][k] * wk(c) + A[r][k+1] * wk1(c)
               const double wkc = __dmul_rn(d21, __dsub_rn(__dmul_rn(d11, e0c), e1c));
               const double wk1c = __dmul_rn(d21, __dsub_rn(__dmul_rn(d22, e1c), e0c));
-              prod = __dadd_rn(__dmul_rn(e0r, wkc), __dmul_rn(e1r, wk1c));
-            } else {       // mirror of A[c][r]: A[c][k] * wk(r) + A[c][k+1] * wk1(r)
-              prod = __dadd_rn(__dmul_rn(e0c, wkr), __dmul_rn(e1c, wk1r));
+              return __dadd_rn(__dmul_rn(e0r, wkc), __dmul_rn(e1r, wk1c));
             }
-            row[c] = __dsub_rn(row[c], prod);
-          }
+            // mirror of A[c][r]: A[c][k] * wk(r) + A[c][k+1] * wk1(r)
+            return __dadd_rn(__dmul_rn(e0c, wkr), __dmul_rn(e1c, wk1r));
+          });
           if (lane == 0) { row[k] = wkr; row[k + 1] = wk1r; }
         }
       }
@@ -358,7 +383,7 @@ int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double
   BkArgs a{const_cast<double*>(S), ld, sS, n, const_cast<int*>(ipiv), sP, active, 0.0, 0};
   const size_t smem = sizeof(double) * (size_t)n;
   static size_t opted = 0;
-  if (smem > 48 * 1024 && smem > opted) {
+  if (smem + 1024 > 48 * 1024 && smem > opted) {  // static shared memory of the kernel counts against the 48 KB default
     const cudaError_t e = cudaFuncSetAttribute(k_bk_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     opted = smem;

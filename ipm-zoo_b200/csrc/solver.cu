@@ -69,6 +69,26 @@ static int dalloc(T** p, size_t count) {
   return IPMZ_OK;
 }
 
+// Page-locked host mirror of the per-problem Scal records: the per-iteration readback is then a true asynchronous
+// D2H copy on the stream's own queue (a pageable destination is staged by the driver and can queue behind the
+// large H2D problem uploads of other sub-batches, which serialises upload and solve).
+struct PinnedScal {
+  Scal* p = nullptr;
+  size_t n = 0;
+  ~PinnedScal() { if (p) cudaFreeHost(p); }
+  bool resize(size_t count) {
+    if (p) cudaFreeHost(p);
+    p = nullptr; n = 0;
+    if (cudaHostAlloc((void**)&p, sizeof(Scal) * (count ? count : 1), cudaHostAllocDefault) != cudaSuccess) return false;
+    std::memset(p, 0, sizeof(Scal) * (count ? count : 1));
+    n = count;
+    return true;
+  }
+  Scal* data() { return p; }
+  Scal& operator[](size_t i) { return p[i]; }
+  const Scal& operator[](size_t i) const { return p[i]; }
+};
+
 // Everything one batch of `count` equally-shaped QPs needs on the device.
 struct Workspace {
   int device = 0, count = 0;
@@ -84,13 +104,14 @@ struct Workspace {
   double* wpanel = nullptr;
   double* MTW = nullptr;  // MT diag(W), B operand of the condensed assembly
   int* ipiv = nullptr;    // [count][ldk] Bunch-Kaufman pivots (EqualityHandling::None: indefinite KKT)
+  int launch_error = 0;   // first cudaError_t a Bunch-Kaufman launcher returned (surfaced by run_ipm / newton_step)
   TrsvWork tw{};
   LookAhead la{};
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
   int Naug = 0;
   int refine = 0;  // iterative-refinement steps of the normal reduction
   // host mirrors
-  std::vector<Scal> sc_host;
+  PinnedScal sc_host;
   std::vector<int> active_host;
   // trace of the last solve (single-problem handles)
   std::vector<double> tr_f, tr_res, tr_mu, tr_alpha_aff, tr_sigma, tr_alpha;
@@ -274,7 +295,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
 #undef ALLOC
   v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
   v.active = nullptr;
-  w->sc_host.resize(count);
+  if (!w->sc_host.resize(count)) return fail(IPMZ_ERR_ALLOC, "cudaHostAlloc of the Scal mirror failed");
   w->active_host.resize(count);
 
   if ((rc = upload_data(*w, p))) return rc;
@@ -349,8 +370,10 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
   if (!v.normal) {
     const FactorPlan fp = plan_of(w, nslots, v.active);
     launch_prepare_sol(w.st, v, nslots, v.rhs, 0);
-    if (s.hard_eq) launch_bk_solve(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, v.sol, v.ssol);
-    else launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
+    if (s.hard_eq) {
+      const int e = launch_bk_solve(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, v.sol, v.ssol);
+      if (e != 0 && w.launch_error == 0) w.launch_error = e;
+    } else launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
   } else {
     condensed_solve(w, v, nslots, v.rhs, 0);
     for (int r = 0; r < w.refine; ++r) {
@@ -372,8 +395,10 @@ static void newton_iteration(Workspace& w, const View& v, int nslots, bool updat
   assemble_and_factor(w, v, nslots);
   const FactorPlan fp = plan_of(w, nslots, v.active);
   // indefinite KKT (zero diagonal block): the reference's solve_indefinite_ hook (Optimizer.cpp:75), Bunch-Kaufman
-  if (v.s.hard_eq) launch_bk_factor(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, 0);
-  else launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
+  if (v.s.hard_eq) {
+    const int e = launch_bk_factor(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, 0);
+    if (e != 0 && w.launch_error == 0) w.launch_error = e;
+  } else launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
   newton_direction(w, v, nslots, 0);
   launch_mu_affine(w.st, v, nslots);
   launch_residuals_rhs(w.st, v, nslots, 1);
@@ -433,6 +458,11 @@ static int run_ipm(Workspace& w, double* ms_out) {
   CUDA_TRY(cudaEventRecord(w.ev1, w.st));
   CUDA_TRY(cudaEventSynchronize(w.ev1));
   CUDA_TRY(cudaGetLastError());
+  if (w.launch_error) {
+    const int e = w.launch_error;
+    w.launch_error = 0;
+    return fail(IPMZ_ERR_CUDA, std::string("Bunch-Kaufman launch: ") + cudaGetErrorString((cudaError_t)e));
+  }
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
   if (ms_out) *ms_out = ms;
@@ -629,6 +659,11 @@ int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* 
   }
   CUDA_TRY(cudaStreamSynchronize(w.st));
   CUDA_TRY(cudaGetLastError());
+  if (w.launch_error) {
+    const int e = w.launch_error;
+    w.launch_error = 0;
+    return fail(IPMZ_ERR_CUDA, std::string("Bunch-Kaufman launch: ") + cudaGetErrorString((cudaError_t)e));
+  }
   if (alpha_aff) *alpha_aff = w.sc_host[0].alpha_aff;
   if (sigma) *sigma = w.sc_host[0].sigma;
   if (alpha) *alpha = w.sc_host[0].alpha;
