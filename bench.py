@@ -325,6 +325,8 @@ def ours(args):
         r = sv.solve()
         it = sv.iterate()
         t1 = time.perf_counter() - t0
+        if rep == 0:  # untimed repetition: HBM-side evidence of the streaming kernels at cfg3 size
+            probe = sv.probe_kernels(20)
         sv.close()
         if rep > 0:
             e2e_runs.append((t1, r))
@@ -336,6 +338,28 @@ def ours(args):
            "device_loop_ms": r.solve_ms,
            "call": "ipmz_create (H2D of Q, A, bounds) + ipmz_solve (full Mehrotra loop, normal reduction) + "
                    "ipmz_get_iterate; flops counted = iterations x (N^3/3 + 4N^2), assembly flops not counted"}
+
+    # achieved HBM GB/s of the streaming kernels (algorithmic bytes / CUDA-event time) against the measured copy peak
+    hbm_peak, hbm_src = 6547.2, "fallback: MEASURED_PEAKS.json absent"
+    try:
+        hbm_peak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                     "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    solve_ms = (step_ms - factor_only_ms) / 2.0
+    hbm_kernels = [{"kernel": "k_trsv_fused (forward + backward sweep of one solve, N=%d)" % N, "ms": solve_ms,
+                    "bytes": float(N) * N * 8.0, "GBps": float(N) * N * 8.0 / (solve_ms * 1e-3) * 1e-9,
+                    "frac": float(N) * N * 8.0 / (solve_ms * 1e-3) * 1e-9 / hbm_peak,
+                    "note": "dependent chain of N/128 block steps: latency-, not bandwidth-bound"}]
+    for name, ms, by in probe:
+        if ms > 0:
+            hbm_kernels.append({"kernel": name, "ms": ms, "bytes": by, "GBps": by / (ms * 1e-3) * 1e-9,
+                                "frac": by / (ms * 1e-3) * 1e-9 / hbm_peak})
+    hbm = {"peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src, "n": n, "m": m,
+           "how": "algorithmic bytes per launch / CUDA-event time over 20 back-to-back launches on the library stream "
+                  "(ipmz_probe_kernels); the three vector passes move < 1 MB and measure launch latency",
+           "kernels": hbm_kernels}
 
     # ---- batched IPM solves/s (cfg4), sharded by problem index, no collective ----
     batched = None
@@ -364,7 +388,7 @@ def ours(args):
                        "l2": "input matrix %.0f MB > 126 MB L2, re-read from HBM every step" % (N * N * 8 / 1e6),
                        "solution_residual": resid, "wall_s": wall},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "batched": batched,
+            "hbm": hbm, "batched": batched,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

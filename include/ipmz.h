@@ -152,6 +152,11 @@ int ipmz_get_trace(ipmz_handle h, int cap, double* f, double* res, double* mu, d
  * dy dz dsl dsu | dlam_y dlam_z dlam_l dlam_u | ds | dx | dlam, absent groups skipped). */
 int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out);
 
+/* Diagnostics for bench.py (HBM roofline of the streaming kernels): CUDA-event time per launch (reps back to back on
+ * the library stream) and algorithmic bytes per launch at the current iterate, 7 slots: k_matvec Q x | k_matvec M x |
+ * k_matvec M^T lambda | k_assemble | k_residuals_rhs<0> | k_backsub_step<0> | k_update (alpha forced to 0). */
+int ipmz_probe_kernels(ipmz_handle h, int reps, double* ms_per_launch, double* bytes_per_launch);
+
 /* ---- mirror of LinearSolvers (host buffers in/out, as the reference's free functions) ---- */
 /* L: n x n unit lower triangular (zeros above the diagonal), D: n pivots; a zero pivot is
  * replaced by 1e-8 (LinearSolvers.cpp:28). */

@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_last_error", "ipmz_version", "ipmz_device_count", "ipmz_default_options", "ipmz_iterate_len",
     "ipmz_host_alloc", "ipmz_host_free", "ipmz_launch_count", "ipmz_fp64_peak_probe",
     "ipmz_create", "ipmz_destroy", "ipmz_set_iterate", "ipmz_get_iterate", "ipmz_reset_iterate",
-    "ipmz_solve", "ipmz_newton_step", "ipmz_get_trace", "ipmz_assemble",
+    "ipmz_solve", "ipmz_newton_step", "ipmz_get_trace", "ipmz_assemble", "ipmz_probe_kernels",
     "ipmz_ldlt_decomposition", "ipmz_overwriting_solve_ldlt",
     "ipmz_symmetric_indefinite_factorization", "ipmz_overwriting_solve_bunch_kaufman",
     "ipmz_factor_create", "ipmz_factor_destroy", "ipmz_factor_set_matrix", "ipmz_factor_set_rhs",
@@ -94,6 +94,7 @@ def lib():
         L.ipmz_newton_step.argtypes = [vp, dp, dp, dp, dp, dp]
         L.ipmz_get_trace.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         L.ipmz_assemble.argtypes = [vp, dp, C.POINTER(C.c_int)]
+        L.ipmz_probe_kernels.argtypes = [vp, C.c_int, dp, dp]
         L.ipmz_ldlt_decomposition.argtypes = [C.c_int, dp, dp, dp]
         L.ipmz_overwriting_solve_ldlt.argtypes = [C.c_int, dp, dp, dp]
         L.ipmz_symmetric_indefinite_factorization.argtypes = [C.c_int, dp, dp, C.POINTER(C.c_int)]
@@ -275,6 +276,15 @@ class Solver:
         return dict(f=f, res=res, mu=mu, alpha_aff=aa[:iterations], sigma=sg[:iterations],
                     alpha=al[:iterations], step_aff=None if sa is None else sa[:iterations],
                     step_cor=None if sc is None else sc[:iterations])
+
+    PROBE_SLOTS = ("k_matvec Q x", "k_matvec M x", "k_matvec M^T lambda", "k_assemble", "k_residuals_rhs<0>",
+                   "k_backsub_step<0>", "k_update")
+
+    def probe_kernels(self, reps=20):
+        """[(kernel, ms per launch, algorithmic bytes per launch)] of the streaming kernels (CUDA events)."""
+        ms, by = np.zeros(7), np.zeros(7)
+        _check(lib().ipmz_probe_kernels(self._h, reps, _ptr(ms), _ptr(by)))
+        return [(self.PROBE_SLOTS[i], float(ms[i]), float(by[i])) for i in range(7)]
 
     def assemble(self):
         N = self.p.N if self.opt.c.reduction != FULL else 5 * self.p.n + 6 * (self.p.N - self.p.n)

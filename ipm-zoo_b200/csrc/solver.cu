@@ -723,6 +723,66 @@ int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out) {
   return IPMZ_OK;
 }
 
+// HBM-side evidence for bench.py: CUDA-event time (library stream, `reps` back-to-back launches after one
+// warm-up) and ALGORITHMIC bytes per launch of the streaming kernels of one iteration, at the handle's current
+// iterate.  Slots: 0 k_matvec Q x | 1 k_matvec M x | 2 k_matvec M^T lambda | 3 k_assemble (+ nothing else) |
+// 4 k_residuals_rhs<0> | 5 k_backsub_step<0> (k_full_unpack<0> for FULL) | 6 k_update with alpha = 0.
+int ipmz_probe_kernels(ipmz_handle h, int reps, double* ms_per_launch, double* bytes_per_launch) {
+  if (!h || reps <= 0 || !ms_per_launch || !bytes_per_launch) return fail(IPMZ_ERR_ARG, "bad argument");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  View v = w.v;
+  v.active = nullptr;
+  const Shape& s = v.s;
+  const double n = s.n, m = s.m, N = v.N;
+  // a consistent state for the kernels that read residuals / directions
+  iteration_matvecs(w, v, 1);
+  launch_residuals_rhs(w.st, v, 1, 0);
+  CUDA_TRY(cudaMemsetAsync(v.sol, 0, sizeof(double) * v.ssol, w.st));
+  if (v.normal) CUDA_TRY(cudaMemsetAsync(v.out, 0, sizeof(double) * (s.ns + s.ms), w.st));
+  auto run = [&](int slot) {
+    switch (slot) {
+      case 0: launch_matvec(w.st, 1, nullptr, v.Q, v.ldq, v.sQ, s.n, s.n, v.V, v.sp, v.Qx, s.ns); break;
+      case 1: if (s.m > 0) launch_matvec(w.st, 1, nullptr, v.M, v.ldm, v.sM, s.m, s.n, v.V, v.sp, v.Mx, s.ms); break;
+      case 2: if (s.m > 0) launch_matvec(w.st, 1, nullptr, v.MT, v.ldmt, v.sMT, s.n, s.m, v.V + (size_t)N_NSLOTS * s.ns, v.sp, v.MTl, s.ns); break;
+      case 3: if (v.full) launch_assemble_full(w.st, v, 1); else launch_assemble(w.st, v, 1); break;
+      case 4: launch_residuals_rhs(w.st, v, 1, 0); break;
+      case 5: if (v.full) launch_full_unpack(w.st, v, 1, 0); else launch_backsub_step(w.st, v, 1, 0); break;
+      case 6: launch_update(w.st, v, 1); break;
+    }
+  };
+  const double pack = (double)v.sp * 8.0;
+  const double bytes[7] = {
+      (n * n + 2 * n) * 8.0, (m * n + n + m) * 8.0, (m * n + n + m) * 8.0,
+      v.full ? (N * N + n * n + 2 * m * n) * 8.0 : v.normal ? (2 * n * n) * 8.0 : (N * N + n * n + 2 * m * n) * 8.0,
+      3.0 * pack,   /* reads V and the matvec results, writes R and the rhs */
+      3.0 * pack,   /* reads V, R and the solution, writes the direction */
+      3.0 * pack};  /* reads V and D, writes V */
+  // the update probe must not move the iterate: alpha = 0 for the duration
+  Scal sc0;
+  CUDA_TRY(cudaMemcpyAsync(&sc0, v.sc, sizeof(Scal), cudaMemcpyDeviceToHost, w.st));
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  Scal scz = sc0;
+  scz.alpha = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(v.sc, &scz, sizeof(Scal), cudaMemcpyHostToDevice, w.st));
+  for (int slot = 0; slot < 7; ++slot) {
+    run(slot);
+    CUDA_TRY(cudaEventRecord(w.ev0, w.st));
+    for (int r = 0; r < reps; ++r) run(slot);
+    CUDA_TRY(cudaEventRecord(w.ev1, w.st));
+    CUDA_TRY(cudaEventSynchronize(w.ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+    ms_per_launch[slot] = (double)ms / reps;
+    bytes_per_launch[slot] = bytes[slot];
+  }
+  CUDA_TRY(cudaMemcpyAsync(v.sc, &sc0, sizeof(Scal), cudaMemcpyHostToDevice, w.st));
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  CUDA_TRY(cudaGetLastError());
+  return IPMZ_OK;
+}
+
 // ---- batch ------------------------------------------------------------------------------
 int ipmz_batch_create(int count, const ipmz_problem* p, const ipmz_options* opt, ipmz_batch_handle* out) {
   if (!out) return fail(IPMZ_ERR_ARG, "null out handle");
