@@ -169,6 +169,8 @@ int ipmz_overwriting_solve_ldlt(int n, const double* L, const double* D, double*
  * bit-exact against the reference (same pivots, same bits); the solve agrees to rounding. */
 int ipmz_symmetric_indefinite_factorization(int n, const double* A, double* LD, int* ipiv);
 int ipmz_overwriting_solve_bunch_kaufman(int n, const double* LD, const int* ipiv, double* b);
+/* Device time (CUDA events) of one Bunch-Kaufman factorization of A, averaged over reps runs from a pristine device copy. */
+int ipmz_bk_factor_time(int n, const double* A, int reps, double* ms_per_factorization);
 
 /* ---- device-resident factor + solve (bench / roofline path) ---- */
 int ipmz_factor_create(int n, int device, ipmz_factor_handle* out);

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_create", "ipmz_destroy", "ipmz_set_iterate", "ipmz_get_iterate", "ipmz_reset_iterate",
     "ipmz_solve", "ipmz_newton_step", "ipmz_get_trace", "ipmz_assemble", "ipmz_probe_kernels",
     "ipmz_ldlt_decomposition", "ipmz_overwriting_solve_ldlt",
-    "ipmz_symmetric_indefinite_factorization", "ipmz_overwriting_solve_bunch_kaufman",
+    "ipmz_symmetric_indefinite_factorization", "ipmz_overwriting_solve_bunch_kaufman", "ipmz_bk_factor_time",
     "ipmz_factor_create", "ipmz_factor_destroy", "ipmz_factor_set_matrix", "ipmz_factor_set_rhs",
     "ipmz_factor_run", "ipmz_factor_profile", "ipmz_factor_get_solution", "ipmz_factor_get_ld",
     "ipmz_factor_info", "ipmz_schedule_check",
@@ -99,6 +99,7 @@ def lib():
         L.ipmz_overwriting_solve_ldlt.argtypes = [C.c_int, dp, dp, dp]
         L.ipmz_symmetric_indefinite_factorization.argtypes = [C.c_int, dp, dp, C.POINTER(C.c_int)]
         L.ipmz_overwriting_solve_bunch_kaufman.argtypes = [C.c_int, dp, C.POINTER(C.c_int), dp]
+        L.ipmz_bk_factor_time.argtypes = [C.c_int, dp, C.c_int, dp]
         L.ipmz_factor_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
         L.ipmz_factor_destroy.argtypes = [vp]
         L.ipmz_factor_set_matrix.argtypes = [vp, dp]
@@ -428,6 +429,14 @@ def symmetric_indefinite_factorization(A):
     ipiv = np.zeros(n, dtype=np.int32)
     _check(lib().ipmz_symmetric_indefinite_factorization(n, _ptr(A), _ptr(LD), ipiv.ctypes.data_as(C.POINTER(C.c_int))))
     return LD, ipiv
+
+
+def bk_factor_time(A, reps=3):
+    """Device ms of one Bunch-Kaufman factorization of A (CUDA events)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    ms = C.c_double()
+    _check(lib().ipmz_bk_factor_time(A.shape[0], _ptr(A), reps, C.byref(ms)))
+    return ms.value
 
 
 def overwriting_solve_bunch_kaufman(LD, ipiv, b):

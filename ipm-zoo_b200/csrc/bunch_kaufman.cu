@@ -18,8 +18,10 @@
 //     row k of the upper one and the pivot searches (column k, row/column imax) and the pivot column of the
 //     rank-1 / rank-2 update are contiguous, coalesced row reads;
 //   * rows are dealt cyclically to the CTAs of a team; one warp updates one row per trip, lanes along the row;
-//   * three team barriers per pivot step (search -> interchange -> update); a single large matrix uses all
-//     SMs (cooperative launch, grid barrier), a batch uses one CTA per matrix (__syncthreads);
+//   * team barriers only where another CTA could still read what one is about to write: one per pivot step while
+//     the pivot is decided on column k alone and no interchange happens (the dominant-diagonal part of a KKT
+//     matrix), three (search -> interchange -> update) otherwise; a single large matrix uses all SMs (cooperative
+//     launch, grid barrier), a batch uses one CTA per matrix (__syncthreads);
 //   * the finished column of L is mirrored into the dead upper row so that the solves read rows, not columns.
 // HBM/L2-bound: the update reads and writes (n-k)^2 doubles per pivot (2 x the lower triangle), i.e.
 // (2/3) n^3 * 8 B of traffic against L2 when the matrix fits (n <= ~3900 in 126 MB), HBM beyond.
@@ -27,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -144,26 +147,34 @@ __global__ void __launch_bounds__(BK_TPB, 1) k_bk_factor(BkArgs a) {
   }
 
   int k = 0;
+  int info = 0;         // LinearSolvers.cpp:103,111-117: only the FIRST zero column records kp = k, later ones keep kp = 0
   int pk = -1, pw = 0;  // previous step: first column and width of the L columns still to be mirrored
   while (k < n) {
     // ---- pivot search: every CTA evaluates it on the same (stable) data ----
     int width = 1, kp = k, imax;
-    bool nothing = false;
+    bool nothing = false, scanned_imax = false;
     double colmax;
     const double akk = fabs(E(k, k));
     block_absmax(S + (size_t)k * ld, k + 1, n, -1, &colmax, &imax, sh_val, sh_arg);
     if (akk == 0.0 && colmax == 0.0) {
       nothing = true;  // column k is zero (LinearSolvers.cpp:111-117)
+      if (info == 0) { info = k; kp = k; } else kp = 0;
     } else if (!(akk >= __dmul_rn(a.alpha, colmax))) {
       double rowmax;
       int dummy;
+      scanned_imax = true;
       block_absmax(S + (size_t)imax * ld, k, n, imax, &rowmax, &dummy, sh_val, sh_arg);
       if (__dmul_rn(akk, rowmax) >= __dmul_rn(__dmul_rn(a.alpha, colmax), colmax)) kp = k;
       else if (fabs(E(imax, imax)) >= __dmul_rn(a.alpha, rowmax)) kp = imax;
       else { kp = imax; width = 2; }
     }
     const int kk = k + width - 1;
-    team_sync<TEAM>();  // nobody still scans the rows the interchange is about to move
+    const bool swap = !nothing && kp != kk;
+    // Barriers only where another CTA could still read what this one is about to write: the interchange moves rows
+    // kk / kp and the update rewrites row imax, both of which other CTAs may still be scanning; a step that decided
+    // on row k alone (the common case while the pivots are dominant) needs neither: row k is not written by the
+    // update, and the mirror below writes rows < k only.
+    if (swap || scanned_imax) team_sync<TEAM>();
 
     // ---- mirror the previous pivot's L column(s) into their (now dead) upper rows, and interchange ----
     if (pk >= 0) {
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(BK_TPB, 1) k_bk_factor(BkArgs a) {
         if (pw == 2) E(pk + 1, r) = E(r, pk + 1);
       }
     }
-    if (!nothing && kp != kk) {
+    if (swap) {
       // symmetric interchange of rows/columns kk and kp of the trailing block S[k:, k:]
       for (int r = first_owned(k) + tid * team; r < n; r += BK_TPB * team) {
         if (r == kk || r == kp) continue;
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(BK_TPB, 1) k_bk_factor(BkArgs a) {
       if (width == 1) ipiv[k] = kp;
       else { ipiv[k] = -kp; ipiv[k + 1] = -kp; }
     }
-    team_sync<TEAM>();
+    if (swap) team_sync<TEAM>();
 
     // ---- trailing update: element (r, c) of S[k+width:, k+width:] with lo = min(r,c), hi = max(r,c) ----
     if (!nothing) {
@@ -433,6 +444,40 @@ int ipmz_symmetric_indefinite_factorization(int n, const double* A, double* LD, 
   CUDA_TRY(cudaMemcpy(ipiv, P.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) LD[(size_t)i * n + j] = (j <= i) ? tmp[(size_t)i * n + j] : A[(size_t)i * n + j];
+  return IPMZ_OK;
+}
+
+/* Device time of one factorization (CUDA events on the launch stream, `reps` factorizations of a pristine device
+ * copy, restore copies outside the timed intervals): the roofline evidence of k_bk_factor in bench.py / tools. */
+int ipmz_bk_factor_time(int n, const double* A, int reps, double* ms_per_factorization) {
+  if (n <= 0 || !A || reps <= 0 || !ms_per_factorization) return ipmz_fail(IPMZ_ERR_ARG, "bad argument");
+  int rc;
+  if ((rc = ipmz_ensure_device(0))) return rc;
+  const int ld = pad4(n);
+  const size_t bytes = sizeof(double) * (size_t)n * ld;
+  DevBuf S, S0, P;
+  CUDA_TRY(cudaMalloc(&S.p, bytes));
+  CUDA_TRY(cudaMalloc(&S0.p, bytes));
+  CUDA_TRY(cudaMalloc(&P.p, sizeof(int) * (size_t)n));
+  CUDA_TRY(cudaMemset(S0.p, 0, bytes));
+  CUDA_TRY(cudaMemcpy2D(S0.p, sizeof(double) * ld, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int r = -1; r < reps; ++r) {  // r = -1: warm-up
+    CUDA_TRY(cudaMemcpyAsync(S.p, S0.p, bytes, cudaMemcpyDeviceToDevice, nullptr));
+    CUDA_TRY(cudaEventRecord(e0, nullptr));
+    CUDA_TRY((cudaError_t)launch_bk_factor(nullptr, 1, nullptr, (double*)S.p, ld, (size_t)n * ld, n, (int*)P.p, (size_t)n, 1));
+    CUDA_TRY(cudaEventRecord(e1, nullptr));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (r >= 0) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_factorization = total / reps;
   return IPMZ_OK;
 }
 

@@ -102,6 +102,30 @@ def test_bk_zero_column_and_nonsymmetric_upper(z):
     check(z, np.ascontiguousarray(K), solve=False)
 
 
+def test_bk_several_zero_columns_keep_the_reference_quirk(z):
+    """LinearSolvers.cpp:103,111-117: only the first zero column (info == 0) records kp = k; later zero columns leave
+    kp = 0, so ipiv[k] = 0 there.  Index parity includes that."""
+    rng = np.random.default_rng(10)
+    n = 48
+    K = sym_indef(rng, n)
+    for j in (5, 20, 33):
+        K[:, j] = 0.0; K[j, :] = 0.0
+    K = np.ascontiguousarray(K)
+    LDo, pivo = oracle_bk(K)
+    assert pivo[5] == 5 and pivo[20] == 0 and pivo[33] == 0
+    check(z, K, solve=False)
+
+
+@pytest.mark.parametrize("n", [64, 300, 1000])
+def test_bk_tied_magnitudes_first_index_wins(z, n):
+    """Entries from {-1, 0, 1}: the pivot searches meet exact ties all the time, and the reference takes the FIRST
+    index of the maximum (strict > scan, LinearSolvers.cpp:86-101)."""
+    rng = np.random.default_rng(n)
+    S = rng.integers(-1, 2, size=(n, n)).astype(np.float64)
+    S = np.tril(S) + np.tril(S, -1).T
+    check(z, np.ascontiguousarray(S), solve=False)
+
+
 def test_bk_empty(z):
     LD, piv = z.symmetric_indefinite_factorization(np.zeros((0, 0)))
     assert LD.shape == (0, 0) and piv.size == 0

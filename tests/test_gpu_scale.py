@@ -33,10 +33,11 @@ def kkt_residuals(p, it):
     return np.linalg.norm(r_x), np.linalg.norm(r_p), np.mean(np.abs(comp)), nonneg.min()
 
 
-def test_cfg2_augmented_vs_normal_n2048(z):
+def test_cfg2_augmented_vs_normal_vs_full_n2048(z):
+    """cfg2 at full size in all three reductions (FULL: 5n + 6m = 16384 unknowns, one 2.1 GB LDL^T per iteration)."""
     p = P.ineq_box(2048, 1024, 2, kind="shift")
     out = {}
-    for red in (z.AUGMENTED, z.NORMAL):
+    for red in (z.AUGMENTED, z.NORMAL, z.FULL):
         s = z.Solver(z.Problem.from_data(p), z.Options(reduction=red))
         r = s.solve()
         it = s.iterate()
@@ -45,11 +46,13 @@ def test_cfg2_augmented_vs_normal_n2048(z):
         rd, rp, mu, mn = kkt_residuals(p, it)
         assert rd < 1e-8 and rp < 1e-8 and mu < 1e-8 and mn > 0.0
         out[red] = (r, it)
-    ra, rn = out[z.AUGMENTED][0], out[z.NORMAL][0]
-    assert ra.iterations == rn.iterations
-    assert abs(ra.f - rn.f) <= 1e-8 * max(1.0, abs(ra.f))
+    ra = out[z.AUGMENTED][0]
     n = p.n
-    assert np.max(np.abs(out[z.AUGMENTED][1][:n] - out[z.NORMAL][1][:n])) < 1e-7
+    for red in (z.NORMAL, z.FULL):
+        rn = out[red][0]
+        assert ra.iterations == rn.iterations
+        assert abs(ra.f - rn.f) <= 1e-8 * max(1.0, abs(ra.f))
+        assert np.max(np.abs(out[z.AUGMENTED][1][:n] - out[red][1][:n])) < 1e-7
 
 
 @pytest.mark.parametrize("n", [1000, 4096])
