@@ -21,4 +21,6 @@ echo "built $HERE/libipmz_b200.so"
   -L"$HERE" -lipmz_b200 -Wl,-rpath,'$ORIGIN'
 /usr/bin/g++ -std=c++17 -O2 -o "$HERE/host/host_demo" "$HERE/host/host_demo.cpp" -L"$HERE" -lipmz_host -lipmz_b200 \
   -Wl,-rpath,'$ORIGIN/..'
-echo "built $HERE/libipmz_host.so and host/host_demo"
+/usr/bin/g++ -std=c++17 -O2 -pthread -o "$HERE/host/ipmz_cli" "$HERE/host/ipmz_cli.cpp" -L"$HERE" -lipmz_host -lipmz_b200 \
+  -Wl,-rpath,'$ORIGIN/..'
+echo "built $HERE/libipmz_host.so, host/host_demo and host/ipmz_cli"

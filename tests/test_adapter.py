@@ -76,3 +76,73 @@ def test_host_cpp_mirror_demo():
     last_iter = [l for l in out.stdout.splitlines() if l.startswith("iter: 12")][0]
     f = float(last_iter.split("f: ")[1].split(",")[0])
     assert abs(f - (-1.12799999999863552e+01)) < 1e-8
+
+
+def _write_qp(path, p):
+    with open(path, "w") as f:
+        f.write("# written by tests/test_adapter.py\nn %d m_ineq %d m_eq %d\n" % (p.n, p.m_ineq, p.m_eq))
+        names = {ol.NONE: "none", ol.LOWER: "lower", ol.UPPER: "upper", ol.BOTH: "both"}
+        f.write("inequalities %s\nvariable_bounds %s\n" % (names[p.ineq_bounds], names[p.var_bounds]))
+        for key, arr in (("Q", p.Q), ("c", p.c), ("A", p.A), ("l_A", p.l_A), ("u_A", p.u_A), ("C", p.C), ("d", p.d),
+                         ("l_x", p.l_x), ("u_x", p.u_x)):
+            if arr is not None and arr.size:
+                f.write(key + "\n" + " ".join(repr(float(v)) for v in np.asarray(arr).ravel()) + "\n")
+
+
+@pytest.mark.gpu
+def test_cli_demo_files_and_batch(tmp_path):
+    """ipm-zoo_b200/host/ipmz_cli: the reference's `IpmZoo -n` demo, a problem file in every
+    reduction, and several files of one shape as one batch -- compared with the reference-generated goldens."""
+    import subprocess
+    exe = os.path.join(ROOT, "ipm-zoo_b200", "host", "ipmz_cli")
+    if not os.path.exists(exe):
+        pytest.skip("ipmz_cli not built")
+    run = lambda *a: subprocess.run([exe] + list(a), capture_output=True, text=True, timeout=120)
+    out = run("-n")
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "iterations: 12 converged: 1" in out.stdout
+    f12 = float([l for l in out.stdout.splitlines() if l.startswith("iter: 12")][0].split("f: ")[1].split(",")[0])
+    assert abs(f12 - (-1.12799999999863552e+01)) < 1e-8
+    # one file, all three reductions, against the golden of the same case
+    p = CASES["ineq_box_20x10"]()
+    g = np.load(os.path.join(GOLD, "ineq_box_20x10.npz"))
+    k = int(g["iterations"])
+    path = str(tmp_path / "p0.qp")
+    _write_qp(path, p)
+    for red in ("augmented", "normal", "full"):
+        out = run("--reduction", red, path)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert ("iterations: %d converged: 1" % k) in out.stdout
+        x = np.array([float(t) for t in [l for l in out.stdout.splitlines() if l.startswith("x:")][0].split()[1:]])
+        assert np.max(np.abs(x - g["iterate"][:p.n])) < 1e-6
+    # equality rows, both handlings
+    q = CASES["eq_box_40x20"]()
+    pq = str(tmp_path / "eq.qp")
+    _write_qp(pq, q)
+    ge = np.load(os.path.join(GOLD, "eq_box_40x20.npz"))
+    for mode in ("slacked", "none"):
+        out = run("--equalities", mode, "--quiet", pq)
+        assert out.returncode == 0, out.stdout + out.stderr
+        x = np.array([float(t) for t in [l for l in out.stdout.splitlines() if l.startswith("x:")][0].split()[1:]])
+        assert np.max(np.abs(x - ge["iterate"][:q.n])) < 1e-6
+    # a batch of three files of one shape
+    import problems as P
+    paths, probs = [], []
+    for i in range(3):
+        probs.append(P.ineq_box(20, 10, 300 + i))
+        paths.append(str(tmp_path / ("b%d.qp" % i)))
+        _write_qp(paths[-1], probs[-1])
+    out = run("--reduction", "normal", *paths)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("problem:")]
+    assert len(lines) == 3
+    for i, l in enumerate(lines):
+        tr = ol.port_solve(probs[i])
+        assert ("iterations: %d, converged: 1" % tr.iterations) in l
+        x = np.array([float(t) for t in l.split("x:")[1].split()])
+        assert np.max(np.abs(x - tr.iterate[:20])) < 1e-6
+    # error convention: unknown keyword -> message on stderr, non-zero exit
+    bad = str(tmp_path / "bad.qp")
+    open(bad, "w").write("n 2 bogus 1\n")
+    out = run(bad)
+    assert out.returncode == 1 and "unknown keyword" in out.stderr
