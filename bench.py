@@ -117,6 +117,14 @@ while True:
             elif len(t) == 3:
                 self.rows.append((float(t[0]), int(t[1]), int(t[2])))
 
+    def wait_ready(self, timeout=90.0):
+        """Block until the helper process has delivered its first sample (a fresh box pages the interpreter and
+        pynvml in slowly), so that the timed region is never entered with a poller that is not polling yet."""
+        t_end = time.time() + timeout
+        while self.proc and self.proc.poll() is None and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+        return bool(self.rows)
+
     def start(self):
         self.t0 = time.time()
 
@@ -124,13 +132,19 @@ while True:
         self.t1 = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["NVML poller unavailable"]}
-        time.sleep(0.01)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         rows = [r for r in self.rows if self.t0 <= r[0] <= self.t1]
+        how = "NVML polled every ms by a helper process; samples inside the timed region"
+        if not rows and self.rows:  # a region shorter than one NVML query: the samples that bracket it
+            before = [r for r in self.rows if r[0] < self.t0][-1:]
+            after = [r for r in self.rows if r[0] > self.t1][:1]
+            rows = before + after
+            how = "NVML polled by a helper process; the timed region was shorter than one query: nearest samples before/after it"
         sm = [r[1] for r in rows]
         bits = 0
         for r in rows:
@@ -138,8 +152,7 @@ while True:
         names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
         reasons = [nm for nm, bit in names if bits & bit]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx if self.mx and self.mx > 0 else None,
-                "samples": len(sm), "reasons": sorted(reasons),
-                "how": "NVML polled every ms by a helper process; samples inside the timed region"}
+                "samples": len(sm), "reasons": sorted(reasons), "how": how}
 
 
 # ------------------------------------------------------------------------------------------
@@ -255,6 +268,7 @@ def ours(args):
     x = fac.solution()
     resid = float(np.max(np.abs(Kc @ x - rhs)) / np.max(np.abs(rhs)))
     launches0 = z.launch_count()
+    sampler.wait_ready()
     barrier()
     sampler.start()
     t0 = time.perf_counter()
@@ -480,7 +494,7 @@ def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sample-n", type=int, default=2048, help="CPU sample size of the reference arm")
