@@ -58,11 +58,16 @@ enum { IPMZ_BOUNDS_NONE = 0, IPMZ_BOUNDS_LOWER = 1, IPMZ_BOUNDS_UPPER = 2, IPMZ_
 enum {
   IPMZ_EQ_OFF = 0,            /* Settings::equalities == false */
   IPMZ_EQ_SLACKED_SLACKS = 1, /* EqualityHandling::SlackedSlacks: C x - t = 0, t - v = d, t + w = d (quasi-definite) */
-  IPMZ_EQ_NONE = 2            /* EqualityHandling::None: C x = d with multiplier lambda_C only
+  IPMZ_EQ_NONE = 2,           /* EqualityHandling::None: C x = d with multiplier lambda_C only
                                  (SymbolicOptimization.cpp:137-140).  The augmented system gets a zero diagonal
                                  block, which the reference routes to solve_indefinite_() == ASSERT(false)
                                  (Optimizer.cpp:63-75); here it is factorized with Bunch-Kaufman pivoting
                                  (LinearSolvers.cpp:76-318 on the device).  AUGMENTED reduction only. */
+  IPMZ_EQ_REGULARIZATION = 3  /* EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): objective +
+                                 1/2 p^T p, rows C x - d + delta p = 0 with delta = ipmz_options.delta_eq.  Eliminating p
+                                 leaves the scalar block -delta^2 I on the diagonal, which the reference's evaluator
+                                 cannot assemble (Evaluation.cpp:53-60); here the rows are quasi-definite like any other.
+                                 p travels in the `t` slot of the packed iterate.  AUGMENTED or NORMAL reduction. */
 };
 
 /* Which reduction of the Newton system is assembled and factorized (north_star). */
@@ -102,6 +107,7 @@ typedef struct {
   int record_steps;            /* keep every iteration's solved Newton steps for ipmz_get_trace */
   int refine_steps;            /* normal reduction: iterative-refinement steps against the augmented
                                   residual per Newton solve; -1 = default (1); ignored for AUGMENTED */
+  double delta_eq;             /* 1e-4   EnvironmentBuilder.cpp:48 (IPMZ_EQ_REGULARIZATION only) */
 } ipmz_options;
 
 typedef struct {

@@ -31,8 +31,9 @@ extern "C" int adapter_solve(int n, int mi, int me, const double* Q, const doubl
     settings.inequalities = bmap[ineq_bounds];
     settings.variable_bounds = bmap[var_bounds];
     settings.equalities = equalities != 0;
-    settings.equality_handling = equalities == 1 ? SymbolicOptimization::EqualityHandling::SlackedSlacks
-                                                 : SymbolicOptimization::EqualityHandling::None;  // 2: None
+    settings.equality_handling = equalities == 1   ? SymbolicOptimization::EqualityHandling::SlackedSlacks
+                                 : equalities == 3 ? SymbolicOptimization::EqualityHandling::Regularization
+                                                   : SymbolicOptimization::EqualityHandling::None;  // 2: None
     const SymbolicOptimization::VariableNames names;
     const auto oe = SymbolicOptimization::get_optimization_expressions(names);
     auto env = build_environment(names, data);

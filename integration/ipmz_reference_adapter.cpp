@@ -72,9 +72,13 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   ASSERT(!ineq || has_var(ns, oe_.s_A_ineq), "inequalities must use InequalityHandling::SlackedSlacks");
   // EqualityHandling::None (SymbolicOptimization.cpp:137-140): the multiplier exists but no equality slack does
   hard_eq_ = eq && !has_var(ns, oe_.s_A_eq) && !v && !w;
-  ASSERT(!eq || hard_eq_ || (v && w && has_var(ns, oe_.s_A_eq)),
-         "equalities must use EqualityHandling::SlackedSlacks or EqualityHandling::None");
-  ASSERT(!has_var(ns, oe_.p_eq), "EqualityHandling::Regularization is not supported");
+  const bool reg_probe = eq && has_var(ns, oe_.p_eq);
+  ASSERT(!eq || hard_eq_ || reg_probe || (v && w && has_var(ns, oe_.s_A_eq)),
+         "equalities must use EqualityHandling::SlackedSlacks, None or Regularization");
+  // EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): p_eq is a variable of the system and the
+  // multiplier's diagonal block is the scalar -delta^2 I; p travels in the `t` slot of the packed iterate
+  reg_eq_ = eq && has_var(ns, oe_.p_eq);
+  if (reg_eq_) hard_eq_ = false;
 
   size_t nq = 0, mi = 0, me = 0;
   const auto Q = flat_matrix(env_, oe_.Q, &nq);
@@ -96,11 +100,15 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   p.l_x = lx.data(); p.u_x = ux.data();
   p.ineq_bounds = !ineq ? IPMZ_BOUNDS_NONE : (g && h) ? IPMZ_BOUNDS_BOTH : g ? IPMZ_BOUNDS_LOWER : IPMZ_BOUNDS_UPPER;
   p.var_bounds = (y && z) ? IPMZ_BOUNDS_BOTH : y ? IPMZ_BOUNDS_LOWER : z ? IPMZ_BOUNDS_UPPER : IPMZ_BOUNDS_NONE;
-  p.equalities = !eq ? IPMZ_EQ_OFF : hard_eq_ ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS;
+  p.equalities = !eq ? IPMZ_EQ_OFF : reg_eq_ ? IPMZ_EQ_REGULARIZATION : hard_eq_ ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = static_cast<int>(reduction);
   opt.device = device;
+  if (reg_eq_ && env_.contains(oe_.delta_eq)) {  // EnvironmentBuilder.cpp:48
+    const auto dv = Evaluation::evaluate(oe_.delta_eq, env_);
+    if (std::holds_alternative<Evaluation::ValScalar>(dv)) opt.delta_eq = std::get<Evaluation::ValScalar>(dv);
+  }
   ipmz_check(ipmz_create(&p, &opt, &handle_));
 }
 
@@ -120,7 +128,7 @@ void B200Optimizer::solve() {
       {oe_.x, n_},
       {oe_.lambda_A_ineq, mi_}, {oe_.s_A_ineq, mi_}, {oe_.lambda_sAineql, mi_}, {oe_.lambda_sAinequ, mi_},
       {oe_.s_A_ineq_l, mi_}, {oe_.s_A_ineq_u, mi_},
-      {oe_.lambda_A_eq, me_}, {oe_.s_A_eq, me_}, {oe_.lambda_sAeql, me_}, {oe_.lambda_sAequ, me_},
+      {oe_.lambda_A_eq, me_}, {reg_eq_ ? oe_.p_eq : oe_.s_A_eq, me_}, {oe_.lambda_sAeql, me_}, {oe_.lambda_sAequ, me_},
       {oe_.s_A_eq_l, me_}, {oe_.s_A_eq_u, me_},
       {oe_.lambda_sxl, n_}, {oe_.lambda_sxu, n_}, {oe_.s_x_l, n_}, {oe_.s_x_u, n_}};
   size_t total = 0;

@@ -42,6 +42,7 @@ class B200Optimizer {
   int n_ = 0, mi_ = 0, me_ = 0;
   int iterations_ = 0;
   bool converged_ = false;
+  bool reg_eq_ = false;   // EqualityHandling::Regularization: p_eq in the system, block -delta^2 I
   bool hard_eq_ = false;  // EqualityHandling::None: lambda_A_eq without s_A_eq -> indefinite KKT, Bunch-Kaufman
 };
 

@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 AUGMENTED, NORMAL, FULL = 0, 1, 2
 NONE, LOWER, UPPER, BOTH = 0, 1, 2, 3
-EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE = 0, 1, 2  # ipmz_problem.equalities (EqualityHandling)
+EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE, EQ_REGULARIZATION = 0, 1, 2, 3  # ipmz_problem.equalities (EqualityHandling)
 dp = C.POINTER(C.c_double)
 
 EXPORTED_SYMBOLS = [
@@ -45,7 +45,7 @@ class _Options(C.Structure):
     _fields_ = [("tolerance", C.c_double), ("max_iter", C.c_int),
                 ("fraction_to_boundary", C.c_double), ("sigma_power", C.c_double),
                 ("reduction", C.c_int), ("device", C.c_int), ("record_steps", C.c_int),
-                ("refine_steps", C.c_int)]
+                ("refine_steps", C.c_int), ("delta_eq", C.c_double)]
 
 
 class _Result(C.Structure):
@@ -207,9 +207,9 @@ class Problem:
 
 class Options:
     def __init__(self, reduction=AUGMENTED, device=0, record_steps=False, tolerance=1e-8, max_iter=100,
-                 fraction_to_boundary=0.995, sigma_power=3.0, refine_steps=-1):
+                 fraction_to_boundary=0.995, sigma_power=3.0, refine_steps=-1, delta_eq=1e-4):
         self.c = _Options(tolerance, max_iter, fraction_to_boundary, sigma_power, reduction, device,
-                          int(record_steps), refine_steps)
+                          int(record_steps), refine_steps, delta_eq)
 
 
 class Result:

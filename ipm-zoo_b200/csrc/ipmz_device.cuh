@@ -36,6 +36,8 @@ struct Shape {
   int clamp_x;       // no g/h slacks in the system -> x also clamped to [l_x, u_x] (Optimizer.cpp:296)
   int ncomp;         // number of complementarity entries (denominator of mu)
   int hard_eq;       // EqualityHandling::None: equality rows carry lambda_C only (no t, v, w) -> indefinite KKT
+  int reg_eq;        // EqualityHandling::Regularization: rows C x - d + delta p = 0, p in the SV slot, block -delta^2 I
+  double delta_eq;
 };
 
 // FULL reduction (un-reduced Newton system, SymbolicOptimization.cpp:417-433): unknowns in the order

@@ -164,7 +164,9 @@ static void fill_shape(Shape& s, const ipmz_problem* p) {
   s.iup = ineq && (p->ineq_bounds == IPMZ_BOUNDS_UPPER || p->ineq_bounds == IPMZ_BOUNDS_BOTH);
   s.clamp_x = ineq ? 0 : 1;
   s.hard_eq = (eq && p->equalities == IPMZ_EQ_NONE) ? 1 : 0;
-  s.ncomp = (s.ilo + s.iup) * s.mi + (s.hard_eq ? 0 : 2 * (s.m - s.mi)) + (s.ylo + s.zup) * s.n;
+  s.reg_eq = (eq && p->equalities == IPMZ_EQ_REGULARIZATION) ? 1 : 0;
+  s.delta_eq = 1e-4;  // overwritten from the options by create_workspace
+  s.ncomp = (s.ilo + s.iup) * s.mi + ((s.hard_eq || s.reg_eq) ? 0 : 2 * (s.m - s.mi)) + (s.ylo + s.zup) * s.n;
 }
 
 // host [rows x cols] dense (count blocks back to back) -> device pitched rows
@@ -243,6 +245,9 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   // the reference routes that to solve_indefinite_() == ASSERT(false) (Optimizer.cpp:63-75).
   if (p->m_eq > 0 && !p->equalities)
     return fail(IPMZ_ERR_INDEFINITE, "equality rows given but Settings::equalities is off");
+  v.s.delta_eq = opt.delta_eq > 0.0 ? opt.delta_eq : 1e-4;
+  if (s.reg_eq && opt.reduction == IPMZ_REDUCTION_FULL)
+    return fail(IPMZ_ERR_ARG, "EqualityHandling::Regularization is available in the AUGMENTED and NORMAL reductions");
   if (s.hard_eq && opt.reduction != IPMZ_REDUCTION_AUGMENTED)
     return fail(IPMZ_ERR_ARG, "EqualityHandling::None (indefinite KKT, Bunch-Kaufman) is available in the AUGMENTED reduction only");
   w->Naug = s.n + s.m;
@@ -541,6 +546,7 @@ void ipmz_default_options(ipmz_options* opt) {
   opt->device = 0;
   opt->record_steps = 0;
   opt->refine_steps = -1;
+  opt->delta_eq = 1e-4;
 }
 
 unsigned long long ipmz_launch_count(void) { return g_launch_count.load(); }

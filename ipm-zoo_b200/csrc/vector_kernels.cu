@@ -133,9 +133,9 @@ __global__ void k_initial_point(View v) {
     nslot(V, s, LAMY)[i] = 1.0; nslot(V, s, LAMZ)[i] = 1.0;
     nslot(V, s, YS)[i] = 1.0; nslot(V, s, ZS)[i] = 1.0;
   }
-  if (i < s.m && s.hard_eq && i >= s.mi) {  // EqualityHandling::None: only the multiplier exists
+  if (i < s.m && (s.hard_eq || s.reg_eq) && i >= s.mi) {  // EqualityHandling::None: only the multiplier exists
     mslot(V, s, LAM)[i] = 1.0;
-    mslot(V, s, SV)[i] = 0.0; mslot(V, s, LAML)[i] = 0.0; mslot(V, s, LAMU)[i] = 0.0;
+    mslot(V, s, SV)[i] = s.reg_eq ? 1.0 : 0.0;  // Regularization: p = 1 (EnvironmentBuilder.cpp:56) mslot(V, s, LAML)[i] = 0.0; mslot(V, s, LAMU)[i] = 0.0;
     mslot(V, s, SL)[i] = 0.0; mslot(V, s, SU)[i] = 0.0;
   } else if (i < s.m) {
     const double mid = 0.5 * (v.lo[(size_t)p * s.ms + i] + v.up[(size_t)p * s.ms + i]);
@@ -240,6 +240,24 @@ __global__ void __launch_bounds__(TPB) k_residuals_rhs(View v) {
       rlam = mslot(R, s, LAM)[i];
     }
     rhs[s.ns + i] = -rlam;
+  } else if (i < s.m && s.reg_eq && i >= s.mi) {
+    // EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): r_lambda = C x - d + delta p,
+    // r_p = p + delta lambda; eliminating dp = -r_p - delta dlambda leaves C dx - delta^2 dlambda = -r_lambda + delta r_p
+    double rlam, rp;
+    if (MODE == 0) {
+      const double pv = mslot(V, s, SV)[i], lam = mslot(V, s, LAM)[i];
+      rlam = (v.Mx[(size_t)p * s.ms + i] + -v.lo[(size_t)p * s.ms + i]) + s.delta_eq * pv;
+      rp = pv + s.delta_eq * lam;
+      mslot(R, s, LAM)[i] = rlam;
+      mslot(R, s, SV)[i] = rp;
+      acc[2] += rlam * rlam + rp * rp;
+      v.winv[(size_t)p * s.ms + i] = s.delta_eq * s.delta_eq;
+      v.W[(size_t)p * s.ms + i] = 1.0 / (s.delta_eq * s.delta_eq);
+    } else {
+      rlam = mslot(R, s, LAM)[i];
+      rp = mslot(R, s, SV)[i];
+    }
+    rhs[s.ns + i] = s.delta_eq * rp + -rlam;
   } else if (i < s.m) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     const double lam = mslot(V, s, LAM)[i], sv = mslot(V, s, SV)[i];
@@ -430,6 +448,10 @@ __global__ void __launch_bounds__(TPB) k_backsub_step(View v) {
   }
   if (i < s.m && s.hard_eq && i >= s.mi) {
     mslot(D, s, LAM)[i] = sol[s.n + i];  // the multiplier is free: no ratio test
+  } else if (i < s.m && s.reg_eq && i >= s.mi) {
+    const double dlam = v.normal ? sol[s.ns + i] : sol[s.n + i];
+    mslot(D, s, LAM)[i] = dlam;
+    mslot(D, s, SV)[i] = -(mslot(Rn, s, SV)[i] + s.delta_eq * dlam);  // dp; both free: no ratio test
   } else if (i < s.m) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     const double dlam = v.normal ? sol[s.ns + i] : sol[s.n + i];
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(TPB) k_mu_affine(View v) {
     if (s.ylo) prod(nslot(V, s, YS)[i], nslot(DA, s, YS)[i], nslot(V, s, LAMY)[i], nslot(DA, s, LAMY)[i]);
     if (s.zup) prod(nslot(V, s, ZS)[i], nslot(DA, s, ZS)[i], nslot(V, s, LAMZ)[i], nslot(DA, s, LAMZ)[i]);
   }
-  if (i < s.m && !(s.hard_eq && i >= s.mi)) {
+  if (i < s.m && !((s.hard_eq || s.reg_eq) && i >= s.mi)) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     if (lo) prod(mslot(V, s, SL)[i], mslot(DA, s, SL)[i], mslot(V, s, LAML)[i], mslot(DA, s, LAML)[i]);
     if (up) prod(mslot(V, s, SU)[i], mslot(DA, s, SU)[i], mslot(V, s, LAMU)[i], mslot(DA, s, LAMU)[i]);

@@ -6,7 +6,7 @@
 //                                            5-variable QP (IpmZoo.cpp:384-408) with -n5
 //   ipmz_cli [options] file.qp [...]         one QP per file; several files of one shape are solved as ONE batch
 //                                            (ipmz_batch_*), sharded by problem index over --devices GPUs
-// options: --reduction augmented|normal|full   --equalities slacked|none   --devices N   --quiet
+// options: --reduction augmented|normal|full   --equalities slacked|none|regularization   --devices N   --quiet
 //
 // Output: the reference's trace lines `iter: k, f: ..., res: ..., gap: ...` (Optimizer.cpp:131-132) with 17 digits
 // for a single problem, then `x: ...`; for a batch one summary line per problem.  Errors follow the reference's
@@ -216,7 +216,8 @@ int main(int argc, char** argv) {
         if (reduction < 0) throw AssertionError("unknown reduction '" + r + "'");
       } else if (a == "--equalities") {
         const std::string r = next();
-        eq_mode = r == "slacked" ? IPMZ_EQ_SLACKED_SLACKS : r == "none" ? IPMZ_EQ_NONE : -1;
+        eq_mode = r == "slacked" ? IPMZ_EQ_SLACKED_SLACKS : r == "none" ? IPMZ_EQ_NONE
+                : r == "regularization" ? IPMZ_EQ_REGULARIZATION : -1;
         if (eq_mode < 0) throw AssertionError("unknown equality handling '" + r + "'");
       } else if (!a.empty() && a[0] == '-') {
         throw AssertionError("unknown option " + a);
@@ -226,7 +227,7 @@ int main(int argc, char** argv) {
     if (demo_which) ps.push_back(demo(demo_which));
     for (const auto& f : files) ps.push_back(read_problem(f));
     if (ps.empty()) {
-      std::cerr << "usage: ipmz_cli -n | [--reduction augmented|normal|full] [--equalities slacked|none] "
+      std::cerr << "usage: ipmz_cli -n | [--reduction augmented|normal|full] [--equalities slacked|none|regularization] "
                    "[--devices N] [--quiet] file.qp [...]" << std::endl;
       return 2;
     }
@@ -234,6 +235,7 @@ int main(int argc, char** argv) {
     if (ps.size() == 1) {
       Problem& p = ps[0];
       if (p.me > 0 && eq_mode == IPMZ_EQ_NONE) p.settings.equality_handling = SO::EqualityHandling::None;
+      if (p.me > 0 && eq_mode == IPMZ_EQ_REGULARIZATION) p.settings.equality_handling = SO::EqualityHandling::Regularization;
       auto env = build_environment(p.data);
       Optimizer optimizer(env, p.data, p.settings, static_cast<Reduction>(reduction));
       optimizer.solve();

@@ -52,6 +52,7 @@ Environment build_environment(const Data& data) {
   Environment env;
   const size_t len[3] = {n, mi, me};
   for (const auto& s : kSlots) env[s.name] = Vector(len[s.kind], 1.0);
+  env["p"] = Vector(me, 1.0);  // EqualityHandling::Regularization (EnvironmentBuilder.cpp:56)
   for (size_t i = 0; i < n; ++i) env["x"][i] = 0.5 * (data.l_x[i] + data.u_x[i]);
   for (size_t i = 0; i < mi && i < data.l_A_ineq.size(); ++i)
     env["s"][i] = 0.5 * (data.l_A_ineq[i] + data.u_A_ineq[i]);
@@ -68,8 +69,11 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   // EqualityHandling::None gives the indefinite KKT matrix the reference routes to solve_indefinite_() ==
   // ASSERT(false) (Optimizer.cpp:63-75); here that hook is implemented with Bunch-Kaufman (AUGMENTED only).
   const bool hard_eq = settings.equalities && settings.equality_handling == EqualityHandling::None;
-  if (settings.equalities && !hard_eq && settings.equality_handling != EqualityHandling::SlackedSlacks)
-    throw AssertionError("Assertion failed: only EqualityHandling::SlackedSlacks is supported");
+  // EqualityHandling::Regularization leaves the scalar block -delta^2 I the reference's evaluator cannot assemble
+  // (Evaluation.cpp:53-60); the library treats those rows as quasi-definite rows (p travels in the `t` slot).
+  reg_eq_ = settings.equalities && settings.equality_handling == EqualityHandling::Regularization;
+  if (settings.equalities && !hard_eq && !reg_eq_ && settings.equality_handling != EqualityHandling::SlackedSlacks)
+    throw AssertionError("Assertion failed: equalities need EqualityHandling::SlackedSlacks, None or Regularization");
   n_ = (int)data.Q.size();
   mi_ = settings.inequalities == Bounds::None ? 0 : (int)data.A_ineq.size();
   me_ = settings.equalities ? (int)data.A_eq.size() : 0;
@@ -85,7 +89,7 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   p.l_x = data.l_x.data(); p.u_x = data.u_x.data();
   p.ineq_bounds = mi_ ? bounds_code(settings.inequalities) : IPMZ_BOUNDS_NONE;
   p.var_bounds = bounds_code(settings.variable_bounds);
-  p.equalities = me_ ? (hard_eq ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS) : IPMZ_EQ_OFF;
+  p.equalities = me_ ? (hard_eq ? IPMZ_EQ_NONE : reg_eq_ ? IPMZ_EQ_REGULARIZATION : IPMZ_EQ_SLACKED_SLACKS) : IPMZ_EQ_OFF;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = (int)reduction;
@@ -101,8 +105,9 @@ void Optimizer::solve() {
   for (const auto& s : kSlots) total += len[s.kind];
   std::vector<double> packed(total, 1.0);
   size_t off = 0;
+  auto key = [&](const Slot& s) { return std::string((reg_eq_ && std::strcmp(s.name, "t") == 0) ? "p" : s.name); };
   for (const auto& s : kSlots) {  // env -> device (warm start: the Environment is the state)
-    auto it = env_.find(s.name);
+    auto it = env_.find(key(s));
     if (it != env_.end() && (int)it->second.size() == len[s.kind])
       std::memcpy(packed.data() + off, it->second.data(), sizeof(double) * len[s.kind]);
     off += len[s.kind];
@@ -121,7 +126,7 @@ void Optimizer::solve() {
   check(ipmz_get_iterate(handle_, packed.data()));
   off = 0;
   for (const auto& s : kSlots) {  // device -> env
-    env_[s.name] = Vector(packed.begin() + off, packed.begin() + off + len[s.kind]);
+    env_[key(s)] = Vector(packed.begin() + off, packed.begin() + off + len[s.kind]);
     off += len[s.kind];
   }
 }

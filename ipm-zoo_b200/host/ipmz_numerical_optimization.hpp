@@ -89,6 +89,7 @@ class Optimizer {
   Environment& env_;
   ipmz_handle handle_ = nullptr;
   int n_ = 0, mi_ = 0, me_ = 0;
+  bool reg_eq_ = false;  // EqualityHandling::Regularization: the `t` slot of the packed iterate carries p
   IterationLog log_;
 };
 

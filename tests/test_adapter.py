@@ -61,6 +61,27 @@ def test_reference_adapter_equality_handling_none():
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SO), reason="adapter test library not prebuilt")
+def test_reference_adapter_equality_handling_regularization():
+    """EqualityHandling::Regularization through the reference's symbolic layer: p_eq is a variable of the Newton
+    system and delta_eq comes from the reference's Environment (EnvironmentBuilder.cpp:48); the reference's own
+    evaluator asserts on the scalar block (Evaluation.cpp:53-60)."""
+    L = C.CDLL(SO)
+    p = CASES["eq_box_40x20"]()
+    g = np.load(os.path.join(GOLD, "eq_box_40x20.npz"))
+    x = np.zeros(p.n)
+    it, conv = C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    P = lambda a: a.ctypes.data_as(dp) if a is not None and a.size else None
+    rc = L.adapter_solve(p.n, 0, p.m_eq, P(p.Q), P(p.c), None, None, None, P(p.C), P(p.d), P(p.l_x), P(p.u_x),
+                         0, p.var_bounds, 3, 0, P(x), C.byref(it), C.byref(conv), err, 512)
+    assert rc == 0, err.value.decode()
+    assert conv.value == 1
+    assert np.max(np.abs(x - g["iterate"][:p.n])) < 1e-5  # delta^2 |lambda| perturbation of the constraint
+    assert np.max(np.abs(p.C @ x - p.d)) < 1e-6
+
+
+@pytest.mark.gpu
 def test_host_cpp_mirror_demo():
     """ipm-zoo_b200/host/host_demo: the reference's demo QP through the C++ host mirror."""
     import subprocess

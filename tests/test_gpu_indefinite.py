@@ -107,3 +107,58 @@ def test_hard_equalities_need_the_augmented_reduction(z):
         with pytest.raises(z.IpmzError) as e:
             z.Solver(hard(z, p), z.Options(reduction=red))
         assert e.value.code == 1
+
+
+# ---- EqualityHandling::Regularization: rows C x - d + delta p = 0, objective + 1/2 p^T p -------------------------
+def reg(z, p):
+    q = z.Problem.from_data(p)
+    q.equalities = z.EQ_REGULARIZATION
+    return q
+
+
+@pytest.mark.parametrize("reduction", [0, 1])
+@pytest.mark.parametrize("n,me", [(8, 3), (40, 20), (200, 100)])
+def test_regularization_newton_step_solves_its_kkt_system(z, n, me, reduction):
+    """The reference derives this system (SymbolicOptimization.cpp:184-192) but cannot assemble its scalar block
+    -delta^2 I (Evaluation.cpp:53-60); the step is checked against the system written out in numpy."""
+    delta = 1e-4
+    p = P.eq_box(n, me, 60 + n)
+    s = z.Solver(reg(z, p), z.Options(reduction=reduction, delta_eq=delta))
+    sa, sc, aa, sg, al = s.newton_step()
+    if reduction == 0:
+        K = s.assemble()
+        assert np.array_equal(K[n:, n:], -delta * delta * np.eye(me))
+    s.close()
+    x = 0.5 * (p.l_x + p.u_x)
+    one, lam, pv = np.ones(n), np.ones(me), np.ones(me)
+    K = np.block([[p.Q + 2.0 * np.eye(n), p.C.T], [p.C, -delta * delta * np.eye(me)]])
+    rx = p.c + one + p.Q @ x + p.C.T @ lam - one
+    ty = 1.0 * (1.0 - 1.0 * ((p.l_x + one) - x))
+    tz = 1.0 * (1.0 - 1.0 * ((x + one) - p.u_x))
+    r_lam = p.C @ x - p.d + delta * pv
+    r_p = pv + delta * lam
+    b = np.concatenate([(tz - rx) - ty, delta * r_p - r_lam])
+    ref = np.linalg.solve(K, b)
+    assert np.max(np.abs(sa - ref)) <= 1e-9 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_regularization_reaches_the_kkt_point_of_the_regularised_qp(z, reduction):
+    delta = 1e-4
+    n, me = 40, 20
+    p = P.eq_box(n, me, 3)
+    ref = ol.port_solve(p)  # the un-regularised optimum (reference, SlackedSlacks)
+    s = z.Solver(reg(z, p), z.Options(reduction=reduction, delta_eq=delta))
+    r = s.solve()
+    it = s.iterate()
+    s.close()
+    assert r.converged and r.iterations <= ref.iterations + 3
+    off = p.offsets()
+    g = lambda k: it[off[k][0]:off[k][0] + off[k][1]]
+    x, lam, pv = it[:n], g("lamC"), g("t")  # p travels in the `t` slot
+    assert np.max(np.abs(p.C @ x - p.d + delta * pv)) < 1e-8
+    assert np.max(np.abs(pv + delta * lam)) < 1e-8
+    assert np.max(np.abs(p.Q @ x + p.c + p.C.T @ lam - g("lamy") + g("lamz"))) < 1e-7
+    # delta^2 |lambda| ~ 1e-8 perturbation of the constraint: the optimum moves by that order
+    assert np.max(np.abs(x - ref.iterate[:n])) < 1e-5
+    assert abs(r.f - ref.f[ref.iterations]) < 1e-5 * max(1.0, abs(r.f))
