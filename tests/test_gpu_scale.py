@@ -232,3 +232,30 @@ print("ok")
     env = dict(os.environ, IPMZ_DATAFLOW_MIN_N="128", PYTHONPATH=root)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_cfg3_full_size_kkt_and_reduction_agreement(z):
+    """cfg3 at BASELINE.json's size (n = 8192, m = 4096): the NORMAL reduction (condensed 8192^2 matrix, the bench
+    workload) and the AUGMENTED one (N = 12288) take the same number of iterations, agree on the objective to 1e-8
+    and on x to 1e-7, and the converged iterate satisfies the KKT conditions to the solver's tolerance."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    d = b.make_cfg3(8192, 4096, b.CFG3["seed"])
+    p = ol.Problem(Q=d["Q"], c=d["c"], A=d["A"], l_A=d["l_A"], u_A=d["u_A"], l_x=d["l_x"], u_x=d["u_x"])
+    out = {}
+    for red in (z.NORMAL, z.AUGMENTED):
+        s = z.Solver(z.Problem.from_data(p), z.Options(reduction=red))
+        r = s.solve()
+        it = s.iterate()
+        s.close()
+        assert r.converged and r.res < 1e-8 and r.mu < 1e-8
+        rd, rp, mu, mn = kkt_residuals(p, it)
+        assert rd < 1e-8 and rp < 1e-8 and mu < 1e-8 and mn > 0.0
+        out[red] = (r, it)
+    rn, ra = out[z.NORMAL][0], out[z.AUGMENTED][0]
+    assert rn.iterations == ra.iterations
+    assert abs(rn.f - ra.f) <= 1e-8 * max(1.0, abs(ra.f))
+    assert np.max(np.abs(out[z.NORMAL][1][:p.n] - out[z.AUGMENTED][1][:p.n])) < 1e-7
