@@ -344,6 +344,144 @@ __global__ void __launch_bounds__(BK_TPB) k_bk_solve(BkArgs a, double* __restric
   for (int i = tid; i < n; i += BK_TPB) x[i] = xs[i];
 }
 
+// Same solve for n <= E * BK_TPB with the global-memory latency taken off the pivot chain: thread t owns the
+// entries i = t + j * BK_TPB of x (j < E); the rows of L^T that the NEXT pivot step needs are prefetched into
+// registers while the current step runs (the factor is final, so the row sequence is known from ipiv alone), the
+// pivots, the 2x2 off-diagonals and ipiv sit in shared memory, and the interchange is folded into the update
+// (the owner of x[kp] substitutes the incoming value), which leaves two block barriers per pivot step.
+template <int E>
+__global__ void __launch_bounds__(BK_TPB, 1) k_bk_solve_fast(BkArgs a, double* __restrict__ xall, size_t sx) {
+  extern __shared__ double sm[];
+  const int n = a.n, ld = a.ld, tid = threadIdx.x;
+  double* xs = sm;            // [n]
+  double* dg = sm + n;        // [n] S(k,k)
+  double* od = sm + 2 * n;    // [n] S(k+1,k) (only read for 2x2 pivots)
+  int* piv = reinterpret_cast<int*>(sm + 3 * n);
+  __shared__ double red[2][BK_WARPS];
+  const int p = a.active ? a.active[blockIdx.y] : (int)blockIdx.y;
+  const double* __restrict__ S = a.S + (size_t)p * a.sS;
+  const int* __restrict__ ipiv = a.ipiv + (size_t)p * a.sP;
+  double* __restrict__ x = xall + (size_t)p * sx;
+  for (int i = tid; i < n; i += BK_TPB) {
+    xs[i] = x[i];
+    dg[i] = S[(size_t)i * ld + i];
+    od[i] = (i + 1 < n) ? S[(size_t)(i + 1) * ld + i] : 0.0;
+    piv[i] = ipiv[i];
+  }
+  // entries of row r owned by this thread, columns > lim only (the rest of the row is not L^T of this pivot)
+  auto fetch = [&](double (&dst)[E], int r, int lim) {
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int i = tid + j * BK_TPB;
+      dst[j] = (r >= 0 && r < n && i > lim && i < n) ? S[(size_t)r * ld + i] : 0.0;
+    }
+  };
+  double c0[E], c1[E], n0[E], n1[E];
+  __syncthreads();
+
+  // ---- forward: L (with interchanges) and D ----
+  int k = 0;
+  fetch(c0, 0, (piv[0] >= 0) ? 0 : 1);
+  fetch(c1, 1, 1);
+  while (k < n) {
+    const bool two = piv[k] < 0;
+    const int w = two ? 2 : 1;
+    const int kn = k + w;
+    const bool ntwo = kn < n && piv[kn] < 0;
+    fetch(n0, kn, ntwo ? kn + 1 : kn);  // in flight while this step runs
+    fetch(n1, kn + 1, kn + 1);
+    if (!two) {
+      const int kp = piv[k];
+      const double bk = xs[kp], bold = xs[k];
+      __syncthreads();
+      const double mlt = -bk;
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int i = tid + j * BK_TPB;
+        if (i > k && i < n) xs[i] = ((i == kp) ? bold : xs[i]) + c0[j] * mlt;
+      }
+      if (tid == 0) xs[k] = bk / dg[k];
+    } else {
+      const int kp = -piv[k];
+      const double b0v = xs[k], b1v = xs[kp], b1old = xs[k + 1];
+      __syncthreads();
+      const double m0 = -b0v, m1 = -b1v;
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int i = tid + j * BK_TPB;
+        if (i > k + 1 && i < n) xs[i] = ((i == kp) ? b1old : xs[i]) + c0[j] * m0 + c1[j] * m1;
+      }
+      if (tid == 0) {
+        const double off = od[k];
+        const double a0 = dg[k] / off, a1 = dg[k + 1] / off;
+        const double den = a0 * a1 - 1.0;
+        const double q0 = b0v / off, q1 = b1v / off;
+        xs[k] = (a1 * q0 - q1) / den;
+        xs[k + 1] = (a0 * q1 - q0) / den;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < E; ++j) { c0[j] = n0[j]; c1[j] = n1[j]; }
+    k = kn;
+  }
+
+  // ---- backward: L^T (with interchanges); the step at k is 2x2 when ipiv[k] < 0 (k = its second row) ----
+  k = n - 1;
+  {
+    const bool two = piv[k] < 0;
+    fetch(c0, k, k);                        // column k
+    fetch(c1, two ? k - 1 : -1, k);         // column k-1 of a 2x2 pivot: entries below the block only
+  }
+  int phase = 0;
+  while (k >= 0) {
+    const bool two = piv[k] < 0;
+    const int kn = k - (two ? 2 : 1);
+    const bool ntwo = kn >= 0 && piv[kn] < 0;
+    fetch(n0, kn, kn);
+    fetch(n1, ntwo ? kn - 1 : -1, kn);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int i = tid + j * BK_TPB;
+      if (i > k && i < n) { s0 += c0[j] * xs[i]; s1 += c1[j] * xs[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    double* rd = red[phase];  // two buffers: the next step's partials never overwrite sums still being read
+    if ((tid & 31) == 0) { rd[tid >> 5] = s0; }
+    __shared__ double red1[2][BK_WARPS];
+    if ((tid & 31) == 0) { red1[phase][tid >> 5] = s1; }
+    __syncthreads();
+    if (tid == 0) {
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < BK_WARPS; ++wi) { t0 += rd[wi]; t1 += red1[phase][wi]; }
+      if (!two) {
+        const int kp = piv[k];
+        const double v = xs[k] - t0;
+        xs[k] = xs[kp]; xs[kp] = v;
+        if (kp == k) xs[k] = v;
+      } else {
+        const int kp = -piv[k];
+        xs[k - 1] -= t1;
+        const double v = xs[k] - t0;
+        xs[k] = xs[kp]; xs[kp] = v;
+        if (kp == k) xs[k] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < E; ++j) { c0[j] = n0[j]; c1[j] = n1[j]; }
+    phase ^= 1;
+    k = kn;
+  }
+  for (int i = tid; i < n; i += BK_TPB) x[i] = xs[i];
+}
+
 // lower triangle (strictly below the diagonal) -> upper triangle, for factors that arrive from the host
 __global__ void k_bk_mirror(double* __restrict__ S, int ld, int n) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -392,6 +530,20 @@ int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double
                     const int* ipiv, size_t sP, double* x, size_t sx) {
   if (n <= 0 || nslots <= 0) return 0;
   BkArgs a{const_cast<double*>(S), ld, sS, n, const_cast<int*>(ipiv), sP, active, 0.0, 0};
+  constexpr int FAST_E = 8;
+  if (n <= FAST_E * BK_TPB) {  // latency-hidden variant: x, pivots and ipiv in shared memory, rows prefetched
+    const size_t smem_fast = sizeof(double) * 3 * (size_t)n + sizeof(int) * (size_t)n;
+    static size_t opted_fast = 0;
+    if (smem_fast + 2048 > 48 * 1024 && smem_fast > opted_fast) {
+      const cudaError_t e =
+          cudaFuncSetAttribute(k_bk_solve_fast<FAST_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+      if (e != cudaSuccess) return (int)e;
+      opted_fast = smem_fast;
+    }
+    k_bk_solve_fast<FAST_E><<<dim3(1, nslots), BK_TPB, smem_fast, st>>>(a, x, sx);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   const size_t smem = sizeof(double) * (size_t)n;
   static size_t opted = 0;
   if (smem + 1024 > 48 * 1024 && smem > opted) {  // static shared memory of the kernel counts against the 48 KB default
