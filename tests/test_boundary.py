@@ -58,3 +58,40 @@ def test_default_options_match_reference_constants(z):
     o = capi._Options()
     z.lib().ipmz_default_options(C.byref(o))
     assert (o.tolerance, o.max_iter, o.fraction_to_boundary, o.sigma_power) == (1e-8, 100, 0.995, 3.0)
+    assert o.delta_eq == 1e-4  # EnvironmentBuilder.cpp:48
+
+
+def test_bunch_kaufman_entry_points_refuse_without_gpu(z):
+    if z.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(z.IpmzError) as e:
+        z.symmetric_indefinite_factorization(np.array([[0.0, 1.0], [1.0, 0.0]]))
+    assert e.value.code == 2
+    with pytest.raises(z.IpmzError):
+        z.bk_factor_time(np.eye(3))
+
+
+def test_cli_host_logic_without_gpu(tmp_path):
+    """ipmz_cli: argument / file parsing is host logic (runs anywhere); a compute request without a CUDA device
+    fails loudly with the library's message -- there is no CPU path behind the CLI either."""
+    import subprocess
+    exe = os.path.join(ROOT, "ipm-zoo_b200", "host", "ipmz_cli")
+    if not os.path.exists(exe):
+        pytest.skip("ipmz_cli not built")
+    run = lambda *a: subprocess.run([exe] + list(a), capture_output=True, text=True, timeout=60)
+    out = run()
+    assert out.returncode == 2 and "usage:" in out.stderr
+    bad = str(tmp_path / "bad.qp")
+    open(bad, "w").write("n 2 # comment\nbogus 1\n")
+    out = run(bad)
+    assert out.returncode == 1 and "unknown keyword 'bogus'" in out.stderr
+    short = str(tmp_path / "short.qp")
+    open(short, "w").write("n 2 m_ineq 0 m_eq 0\nQ 1 0 0\n")
+    out = run(short)
+    assert out.returncode == 1 and "unexpected end" in out.stderr
+    out = run("--reduction", "cholesky", "-n")
+    assert out.returncode == 1 and "unknown reduction" in out.stderr
+    import ipm_zoo_b200 as zz
+    if zz.device_count() == 0:
+        out = run("-n")
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
