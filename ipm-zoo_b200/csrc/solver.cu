@@ -110,6 +110,8 @@ struct Workspace {
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
   int Naug = 0;
   int refine = 0;  // iterative-refinement steps of the normal reduction
+  int refine_extra = 0;   // +1 on the late iterations of a single QP (run_ipm), see there
+  bool refine_auto = false;
   // host mirrors
   PinnedScal sc_host;
   std::vector<int> active_host;
@@ -264,6 +266,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.tol = opt.tolerance; v.ftb = opt.fraction_to_boundary; v.sigma_pow = opt.sigma_power;
   v.max_iter = opt.max_iter;
   w->refine = v.normal ? (opt.refine_steps < 0 ? 1 : opt.refine_steps) : 0;
+  w->refine_auto = v.normal && opt.refine_steps < 0;
   const int len = std::max(s.ns, s.ms);
   v.maxblk = (len + 255) / 256;
 
@@ -381,7 +384,7 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
     } else launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
   } else {
     condensed_solve(w, v, nslots, v.rhs, 0);
-    for (int r = 0; r < w.refine; ++r) {
+    for (int r = 0; r < w.refine + w.refine_extra; ++r) {
       const size_t so = (size_t)s.ns + s.ms;
       launch_matvec(w.st, nslots, v.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.out, so, v.Qd, s.ns);
       if (s.m > 0) {
@@ -458,8 +461,14 @@ static int run_ipm(Workspace& w, double* ms_out) {
     }
     if (nact == 0) break;
     v.active = identity ? nullptr : w.active_dev;
+    // NORMAL reduction, single QP, default refinement: one step of refinement leaves a relative step error of about
+    // (cond * eps)^2, and cond(Hx + M^T W M) grows like 1/mu; on the last iterations of an ill-conditioned QP (cfg5:
+    // res lands at 1.05e-8 against the reference's 8.19e-9 and the 1e-8 tolerance) that is not enough to follow the
+    // reference's augmented step, so the late iterations take a second step (two more solves out of ~11 x 4).
+    w.refine_extra = (count == 1 && w.refine_auto && w.sc_host[0].mu < 1e-6) ? 1 : 0;
     newton_iteration(w, v, nact, true, (count == 1 && w.opt.record_steps) ? it : -1);
   }
+  w.refine_extra = 0;
   CUDA_TRY(cudaEventRecord(w.ev1, w.st));
   CUDA_TRY(cudaEventSynchronize(w.ev1));
   CUDA_TRY(cudaGetLastError());

@@ -3,6 +3,8 @@
 // :361-378).  All kernels are HBM-bound streaming passes over the packed iterate; the
 // reductions (objective, residual norm, mean complementarity, step-length minimum) use warp
 // shuffles inside a block and a deterministic last-block finish across blocks.
+#include <cstdlib>
+
 #include "ipmz_device.cuh"
 #include "ipmz_kernels.h"
 
@@ -71,35 +73,72 @@ __device__ void reduce_finish(double (&v)[K], const View& vw, Fin fin) {
 
 }  // namespace
 
-// y[r] = dot(A[r][0:cols], x) for one matrix per problem; one warp per row, 16-byte loads.
-// Used for Q x, M x, M^T lambda, M^T (W b1), M dx -- the only O(n^2)-byte movers outside the
-// factorization (reference: Evaluation.cpp:35-41).
+// y[r] = dot(A[r][0:cols], x) for one matrix per problem.  Used for Q x, M x, M^T lambda, M^T (W b1), M dx -- the
+// only O(n^2)-byte movers outside the factorization (reference: Evaluation.cpp:35-41).  HBM-bound streaming:
+// one warp per row with U = 8 independent 16-byte loads in flight per lane (the pass needs ~5 MB in flight per GPU at
+// HBM latency), the matrix read with the streaming (evict-first) policy and x through the read-only path so the
+// rows flowing through L1 do not evict the vector every warp re-reads, and CTAs small enough that every SM gets at
+// least ~6 of them (a 4096-row matrix on 8-warp CTAs left 3.46 CTAs per SM: 59 % of the copy peak against 88 % for
+// 8192 rows).  Several rows per warp were measured and dropped: fewer, fatter warps lose more than the x re-use wins
+// (Q x at n = 8192: 1 row 5.8 TB/s, 2 rows 4.9, 4 rows 4.2; `tools/matvec_ab.py`).
+// Long rows are split over 2 or 4 warps (a function of `cols` only): a warp that issues 8 loads and then waits for
+// them keeps about half of them in flight on average, and 4096 such warps are too few to fill HBM (M x at cfg3 size:
+// 3.9 TB/s with one warp per 64 KB row).
+// The accumulation order of a row (chunks in order; inside a chunk two accumulators by trip parity, then the warp
+// tree) depends on `cols` alone, never on the batch, so a QP gets bitwise the same products alone, in a batch or in
+// a sub-batch.
+template <int U>
 __global__ void __launch_bounds__(TPB) k_matvec(const double* __restrict__ A, int lda, size_t sA, int rows,
                                                 int cols, const double* __restrict__ x, size_t sx,
                                                 double* __restrict__ y, size_t sy,
-                                                const int* __restrict__ active) {
+                                                const int* __restrict__ active, int split) {
+  static_assert(U % 2 == 0, "trip parity = unroll parity");
+  __shared__ double part_sum[TPB / 32];
   const int p = active ? active[blockIdx.y] : blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const double2* a2 = reinterpret_cast<const double2*>(A + (size_t)p * sA + (size_t)row * lda);
-  const double2* x2 = reinterpret_cast<const double2*>(x + (size_t)p * sx);
-  const int c2 = (cols + 1) >> 1;
-  double acc0 = 0.0, acc1 = 0.0;
-  int k = lane;
-  for (; k + 32 < c2; k += 64) {
-    const double2 a = a2[k], b = a2[k + 32];
-    const double2 u = x2[k], w = x2[k + 32];
-    acc0 = fma(a.x, u.x, acc0); acc0 = fma(a.y, u.y, acc0);
-    acc1 = fma(b.x, w.x, acc1); acc1 = fma(b.y, w.y, acc1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // `split` warps share one long row (a function of cols only, see launch_matvec): each takes a contiguous chunk
+  const int row = blockIdx.x * ((blockDim.x >> 5) / split) + wid / split;
+  const int part = wid % split;
+  const bool valid = row < rows;
+  double sres = 0.0;
+  if (valid) {
+    const double2* a2 = reinterpret_cast<const double2*>(A + (size_t)p * sA + (size_t)row * lda);
+    const double2* x2 = reinterpret_cast<const double2*>(x + (size_t)p * sx);
+    const int c2 = (cols + 1) >> 1;
+    const int chunk = (((c2 + split - 1) / split) + 63) & ~63;
+    const int k0 = part * chunk, k1 = min(c2, k0 + chunk);
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int k = k0 + lane; k < k1; k += 32 * U) {
+      double2 av[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kk = k + 32 * u;
+        const bool in = kk < k1;
+        xv[u] = in ? __ldg(x2 + kk) : make_double2(0.0, 0.0);
+        av[u] = in ? __ldcs(a2 + kk) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + 32 * u < k1) {
+          double& t = (u & 1) ? acc1 : acc0;
+          t = fma(av[u].x, xv[u].x, t);
+          t = fma(av[u].y, xv[u].y, t);
+        }
+      }
+    }
+    sres = warp_sum(acc0 + acc1);
   }
-  for (; k < c2; k += 32) {
-    const double2 a = a2[k];
-    const double2 u = x2[k];
-    acc0 = fma(a.x, u.x, acc0); acc0 = fma(a.y, u.y, acc0);
+  if (split == 1) {
+    if (valid && lane == 0) y[(size_t)p * sy + row] = sres;
+    return;
   }
-  const double s = warp_sum(acc0 + acc1);
-  if (lane == 0) y[(size_t)p * sy + row] = s;
+  if (lane == 0) part_sum[wid] = sres;
+  __syncthreads();
+  if (valid && part == 0 && lane == 0) {
+    double t = part_sum[wid];
+    for (int q = 1; q < split; ++q) t += part_sum[wid + q];  // fixed order: chunk 0, 1, ...
+    y[(size_t)p * sy + row] = t;
+  }
 }
 
 // Tiled transpose M [m x n] -> MT [n x m], once per problem upload.
@@ -537,8 +576,15 @@ __global__ void k_update(View v) {
 void launch_matvec(cudaStream_t st, int nslots, const int* active, const double* A, int lda, size_t sA,
                    int rows, int cols, const double* x, size_t sx, double* y, size_t sy) {
   if (rows <= 0 || nslots <= 0) return;
-  dim3 grid((rows + 7) / 8, nslots);
-  k_matvec<<<grid, TPB, 0, st>>>(A, lda, sA, rows, cols, x, sx, y, sy, active); count_launch();
+  const int split = cols >= 8192 ? 4 : cols >= 2048 ? 2 : 1;  // warps per row: by cols only (bitwise stable per shape)
+  // warps per CTA: 8, or fewer when that would leave an SM with less than ~6 CTAs to balance
+  const long long total = (long long)rows * nslots * split;
+  int w = total >= 8LL * 148 * 6 ? 8 : total >= 4LL * 148 * 6 ? 4 : 2;
+  if (w < split) w = split;
+  const int rows_per_cta = w / split;
+  k_matvec<8><<<dim3((rows + rows_per_cta - 1) / rows_per_cta, nslots), 32 * w, 0, st>>>(A, lda, sA, rows, cols, x, sx, y,
+                                                                                         sy, active, split);
+  count_launch();
 }
 
 void launch_transpose(cudaStream_t st, int count, const double* M, int ldm, size_t sM, double* MT, int ldmt,
