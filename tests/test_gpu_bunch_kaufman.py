@@ -78,6 +78,19 @@ def test_bk_large_team_bit_exact(z):
     check(z, sym_indef(np.random.default_rng(5), 1500), seed=1)
 
 
+def test_bk_solve_beyond_the_prefetching_kernel(z):
+    """n > 4096 takes the plain one-CTA solve (x alone in shared memory, opt-in above 48 KB): residual check
+    against the matrix, the factor comes from the device as well."""
+    rng = np.random.default_rng(12)
+    K = saddle(rng, 3000, 1400)
+    n = K.shape[0]
+    LD, piv = z.symmetric_indefinite_factorization(K)
+    b = rng.standard_normal(n)
+    x = b.copy()
+    z.overwriting_solve_bunch_kaufman(LD, piv, x)
+    assert np.max(np.abs(K @ x - b)) <= 1e-8 * max(1.0, np.max(np.abs(x)))
+
+
 def test_bk_golden_reference_vectors(z):
     g = np.load(os.path.join(GOLD, "linear_solvers.npz"))
     for nm in ("indef", "quasidef"):
