@@ -515,7 +515,7 @@ int factor_init() {
 
 static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout,
                              int ldc, size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb,
-                             size_t sB, int rows, int kdim, double sign, int mode, int fcols) {
+                             size_t sB, int rows, int kdim, double sign, int mode, int fcols, bool side_stream) {
   if (rows <= 0 || kdim <= 0 || nslots <= 0) return;
   if (g_num_sms == 0) {
     int dev = 0;
@@ -530,7 +530,9 @@ static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, con
     else { const int U = T - fcols; tiles = U > 0 ? U * (U + 1) / 2 : 0; }
     if (tiles <= 0) return;
     SyrkArgs a{Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, active, 0, mode, fcols, tiles};
-    int ctas = g_num_sms - g_ws_reserve;
+    // SMs are left free only when a side stream runs panel kernels next to this launch (look-ahead schedule); the
+    // condensed assembly owns the GPU: 2080 tiles at n = 8192 are 16 rounds on 132 CTAs, 15 on 148
+    int ctas = g_num_sms - (side_stream ? g_ws_reserve : 0);
     if (ctas < 1) ctas = 1;
     if (ctas > tiles) ctas = tiles;
     k_syrk_ws<<<ctas, WS_THREADS, WS_SMEM, st>>>(a); count_launch();
@@ -556,7 +558,7 @@ static void launch_syrk_mode(cudaStream_t st, int nslots, const int* active, con
 void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const double* Cin, double* Cout, int ldc,
                      size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb, size_t sB, int rows,
                      int kdim, double sign) {
-  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, 0, 0);
+  launch_syrk_mode(st, nslots, active, Cin, Cout, ldc, sC, PA, lda, sA, PB, ldb, sB, rows, kdim, sign, 0, 0, false);
 }
 
 // Optional per-launch instrumentation (bench roofline): events around every kernel.
@@ -612,7 +614,7 @@ static void launch_trailing(cudaStream_t st, const FactorPlan& fp, const double*
   hk.begin(st, 2);
   launch_syrk_mode(st, fp.nslots, fp.active, in + off, dst + off, fp.ld, fp.sK, dst + (size_t)c0 * fp.ld + p0,
                    fp.ld, fp.sK, wpanel_of(fp, p0) + (size_t)c0 * WLD + (p0 % WLD), WLD, fp.sW, rem, kdim, -1.0, mode,
-                   fcols);
+                   fcols, fp.la != nullptr);
   hk.end(st);
   if (hk.flops_syrk) {
     // algorithmic flops: lower triangle of the updated region, 2 flops per multiply-add
