@@ -106,8 +106,8 @@ typedef struct {
   int device;                  /* CUDA device ordinal */
   int record_steps;            /* keep every iteration's solved Newton steps for ipmz_get_trace */
   int refine_steps;            /* normal reduction: iterative-refinement steps against the augmented
-                                  residual per Newton solve; -1 = default (1, and 2 on the iterations of a
-                                  single QP with mu < 1e-6); ignored for AUGMENTED */
+                                  residual per Newton solve; -1 = default policy by each problem's mu (none while
+                                  mu >= 1e-3, then 1; 2 for a single QP once mu < 1e-6); ignored for AUGMENTED */
   double delta_eq;             /* 1e-4   EnvironmentBuilder.cpp:48 (IPMZ_EQ_REGULARIZATION only) */
 } ipmz_options;
 

@@ -26,6 +26,8 @@ void launch_aug_residual(cudaStream_t st, const View& v, int nslots);
 void launch_backsub_step(cudaStream_t st, const View& v, int nslots, int mode);
 void launch_mu_affine(cudaStream_t st, const View& v, int nslots);
 void launch_update(cudaStream_t st, const View& v, int nslots);
+// out <- the problems among the first nact active ones whose mu < thr (compacted, in slot order)
+void launch_refine_list(cudaStream_t st, const View& v, int nact, double thr, int* out);
 
 // ---- assemble.cu ----
 // Augmented KKT [[Q + Y^-1 L_y + Z^-1 L_z, M^T],[M, -W^-1]] (full symmetric, N = n+m) or the

@@ -112,6 +112,10 @@ struct Workspace {
   int refine = 0;  // iterative-refinement steps of the normal reduction
   int refine_extra = 0;   // +1 on the late iterations of a single QP (run_ipm), see there
   bool refine_auto = false;
+  // problems of the current iteration that take refinement steps (default policy: those with mu < 1e-3)
+  int* refine_dev = nullptr;  // [count] compacted on the device by k_refine_list
+  int nref = 0;               // how many (counted on the host from the same Scal records)
+  bool refine_all = true;     // every active problem refines: the kernels run on the active list itself
   // host mirrors
   PinnedScal sc_host;
   std::vector<int> active_host;
@@ -296,6 +300,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (v.normal) ALLOC(w->MTW, C * v.sMT);
   ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
   ALLOC(w->active_dev, C);
+  ALLOC(w->refine_dev, C);
   if (s.hard_eq) ALLOC(w->ipiv, C * v.ldk);
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
@@ -384,19 +389,47 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
     } else launch_ldlt_solve(w.st, fp, v.K, v.Dg, v.sol, v.ssol, w.tw);
   } else {
     condensed_solve(w, v, nslots, v.rhs, 0);
-    for (int r = 0; r < w.refine + w.refine_extra; ++r) {
+    // refinement runs on the problems that need it only (per-problem decision, so a QP sees the same arithmetic
+    // alone, in a batch or in a sub-batch)
+    View vr = v;
+    int nr = nslots;
+    if (!w.refine_all) { vr.active = w.refine_dev; nr = w.nref; }
+    for (int r = 0; nr > 0 && r < w.refine + w.refine_extra; ++r) {
       const size_t so = (size_t)s.ns + s.ms;
-      launch_matvec(w.st, nslots, v.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.out, so, v.Qd, s.ns);
+      launch_matvec(w.st, nr, vr.active, v.Q, v.ldq, v.sQ, s.n, s.n, v.out, so, v.Qd, s.ns);
       if (s.m > 0) {
-        launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.out + s.ns, so, v.tn, s.ns);
+        launch_matvec(w.st, nr, vr.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.out + s.ns, so, v.tn, s.ns);
         // first refinement step: out's dx is still the vector the condensed solve just multiplied by M (v.Mx)
-        if (r > 0) launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.out, so, v.Mx, s.ms);
+        if (r > 0) launch_matvec(w.st, nr, vr.active, v.M, v.ldm, v.sM, s.m, s.n, v.out, so, v.Mx, s.ms);
       }
-      launch_aug_residual(w.st, v, nslots);
-      condensed_solve(w, v, nslots, v.resid, 1);
+      launch_aug_residual(w.st, vr, nr);
+      condensed_solve(w, vr, nr, v.resid, 1);
     }
   }
   launch_backsub_step(w.st, v, nslots, mode);
+}
+
+// Which of the `nact` active problems refine their condensed solves in this iteration.  Default policy
+// (options.refine_steps < 0): those with mu < 1e-3.  Without refinement the condensed step differs from the augmented
+// one by about eps * max(W) ~ eps / mu: measured over every golden case and iteration <= 4e-12 relative for
+// mu >= 1e-3 and 2e-11 on cfg5 at full size (n = 4096, the ill-conditioned config): 50x below the 1e-9 parity
+// bound; it reaches 1e-9 .. 1e-4 for mu below 1e-5 (tests/test_refinement_policy.py),
+// so the first ~4 of ~9-11 iterations skip two of their four solves and eight of their fifteen matrix passes.
+// Needs w.sc_host = the Scal records of this iteration (read back by the caller).
+static void select_refinement(Workspace& w, const View& v, int nact) {
+  w.refine_all = true;
+  w.nref = nact;
+  if (!v.normal || !w.refine_auto || w.refine + w.refine_extra <= 0) return;
+  if (v.s.reg_eq) return;  // EqualityHandling::Regularization: W = 1 / delta^2 is huge from the first iterate on
+  const double thr = 1e-3;
+  int n = 0;
+  for (int i = 0; i < nact; ++i) {
+    const int q = v.active ? w.active_host[i] : i;
+    if (w.sc_host[q].mu < thr) ++n;
+  }
+  w.nref = n;
+  w.refine_all = (n == nact);
+  if (!w.refine_all && n > 0) launch_refine_list(w.st, v, nact, thr, w.refine_dev);
 }
 
 static void newton_iteration(Workspace& w, const View& v, int nslots, bool update, int record_iter) {
@@ -466,9 +499,11 @@ static int run_ipm(Workspace& w, double* ms_out) {
     // res lands at 1.05e-8 against the reference's 8.19e-9 and the 1e-8 tolerance) that is not enough to follow the
     // reference's augmented step, so the late iterations take a second step (two more solves out of ~11 x 4).
     w.refine_extra = (count == 1 && w.refine_auto && w.sc_host[0].mu < 1e-6) ? 1 : 0;
+    select_refinement(w, v, nact);
     newton_iteration(w, v, nact, true, (count == 1 && w.opt.record_steps) ? it : -1);
   }
   w.refine_extra = 0;
+  w.refine_all = true;
   CUDA_TRY(cudaEventRecord(w.ev1, w.st));
   CUDA_TRY(cudaEventSynchronize(w.ev1));
   CUDA_TRY(cudaGetLastError());
@@ -661,7 +696,15 @@ int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* 
   const Shape& s = v.s;
   iteration_matvecs(w, v, 1);
   launch_residuals_rhs(w.st, v, 1, 0);
+  if (v.normal) {  // the refinement policy of run_ipm, from this iterate's mu
+    CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal), cudaMemcpyDeviceToHost, w.st));
+    CUDA_TRY(cudaStreamSynchronize(w.st));
+    w.refine_extra = (w.refine_auto && w.sc_host[0].mu < 1e-6) ? 1 : 0;
+    select_refinement(w, v, 1);
+  }
   newton_iteration(w, v, 1, false, -1);
+  w.refine_extra = 0;
+  w.refine_all = true;
   CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal), cudaMemcpyDeviceToHost, w.st));
   double* outs[2] = {step_aff, step_cor};
   const double* packs[2] = {v.DA, v.D};

@@ -605,6 +605,22 @@ __global__ void k_update(View v) {
   if (i == 0) v.sc[p].iters += 1;
 }
 
+// Compaction of the active problems that refine their condensed solves (mu < thr) -- one warp, ballot + prefix;
+// the host counts the same predicate on the Scal records it has just read, so only the list stays on the device
+// (an H2D copy here would queue behind the problem uploads of other sub-batches).
+__global__ void k_refine_list(View v, int nact, double thr, int* __restrict__ out) {
+  const int lane = threadIdx.x;
+  int base_out = 0;
+  for (int base = 0; base < nact; base += 32) {
+    const int i = base + lane;
+    const int p = i < nact ? (v.active ? v.active[i] : i) : 0;
+    const bool need = i < nact && v.sc[p].mu < thr;
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (need) out[base_out + __popc(m & ((1u << lane) - 1u))] = p;
+    base_out += __popc(m);
+  }
+}
+
 // ---- host-side launchers --------------------------------------------------------------
 void launch_matvec(cudaStream_t st, int nslots, const int* active, const double* A, int lda, size_t sA,
                    int rows, int cols, const double* x, size_t sx, double* y, size_t sy) {
@@ -666,6 +682,9 @@ void launch_backsub_step(cudaStream_t st, const View& v, int nslots, int mode) {
 }
 void launch_mu_affine(cudaStream_t st, const View& v, int nslots) {
   k_mu_affine<<<vec_grid(v, nslots), TPB, 0, st>>>(v); count_launch();
+}
+void launch_refine_list(cudaStream_t st, const View& v, int nact, double thr, int* out) {
+  k_refine_list<<<1, 32, 0, st>>>(v, nact, thr, out); count_launch();
 }
 void launch_update(cudaStream_t st, const View& v, int nslots) {
   dim3 grid((unsigned)((v.sp + TPB - 1) / TPB), nslots);
