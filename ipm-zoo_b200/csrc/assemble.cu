@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(32 * AS_ROWS) k_assemble(View v) {
 __global__ void __launch_bounds__(32 * AS_ROWS) k_scale_cols(const double* __restrict__ in, double* __restrict__ out,
                                                              int ld, size_t sM, int rows, int cols,
                                                              const double* __restrict__ d, size_t sd,
-                                                             const int* __restrict__ active) {
+                                                             const int* __restrict__ active, double sign) {
   const int p = active ? active[blockIdx.y] : blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * AS_ROWS + (threadIdx.x >> 5);
@@ -71,15 +71,15 @@ __global__ void __launch_bounds__(32 * AS_ROWS) k_scale_cols(const double* __res
   // ld and the stride of d are multiples of 4 and the padding of `in` is zero: whole double2's
   for (int c = lane; c < (cols + 1) >> 1; c += 32) {
     const double2 a = src[c], w = dv[c];
-    dst[c] = make_double2(a.x * w.x, 2 * c + 1 < cols ? a.y * w.y : 0.0);
+    dst[c] = make_double2(sign * (a.x * w.x), 2 * c + 1 < cols ? sign * (a.y * w.y) : 0.0);
   }
 }
 
 void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
-                       size_t sM, int rows, int cols, const double* d, size_t sd) {
+                       size_t sM, int rows, int cols, const double* d, size_t sd, double sign) {
   if (rows <= 0 || cols <= 0 || nslots <= 0) return;
   k_scale_cols<<<dim3((rows + AS_ROWS - 1) / AS_ROWS, nslots), 32 * AS_ROWS, 0, st>>>(in, out, ld, sM, rows, cols, d, sd,
-                                                                                     active);
+                                                                                     active, sign);
   count_launch();
 }
 

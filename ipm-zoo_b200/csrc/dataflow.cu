@@ -28,6 +28,8 @@ namespace ipmz {
 
 int dataflow_tma_init();
 int dataflow_tma_launch(cudaStream_t st, const void* args, int ctas, const double* W);
+int dataflow_tma_launch_operands(cudaStream_t st, const void* args, int ctas, const double* A, int rowsA, int ldA,
+                                 const double* B, int rowsB, int ldB);
 
 int dataflow_init() {
   const int e = df_kernel_init();
@@ -167,6 +169,82 @@ int launch_ldlt_dataflow_logged(cudaStream_t st, DataflowPlan& p, const double* 
   const int n = p.ntasks < cap_tasks ? p.ntasks : cap_tasks;
   e = cudaMemcpy(host_log, p.d_tlog, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost);
   *ntasks = n;
+  return (int)e;
+}
+
+// ---- condensed assembly K += MT diag(W) MT^T on the dataflow kernel ----------------------------------------------
+// The UPD task of the factorization computes C(i,j) -= A(i, k0..k1) B(j, k0..k1)^T on 128 x 128 tiles with TMA-fed
+// operands; the condensed assembly is the same contraction with A = MT (n x m) and B = -MT diag(W), every input ready
+// from the start.  So it runs as a list of UPD tasks only: `rdy` flags preset, the tile counter `cnt` orders the
+// chunks of one tile (at most 15 panels each), chunk-major order keeps those chunks far apart in the ticket queue,
+// and the ticket queue balances the 148 CTAs dynamically (the persistent SYRK kernel assigns tiles round-robin and
+// ends with a round of 8 tiles at n = 8192).
+struct AssemblyPlan {
+  int n = 0, m = 0, nt = 0, ntasks = 0, nsm = 0;
+  int4* d_tasks = nullptr;
+  int* d_flags = nullptr;  // [0] ticket, [1] abort, [2] sticky, [3] pad, then rdy[nt*nt], cnt[nt*nt]
+  size_t flag_ints = 0;
+};
+
+int dataflow_assembly_plan_create(AssemblyPlan** out, int n, int m) {
+  *out = nullptr;
+  static const int enabled = env_int("IPMZ_ASM_DATAFLOW", 1);
+  const int nt = (n + DF_TILE - 1) / DF_TILE, P = (m + DF_TILE - 1) / DF_TILE;
+  if (!enabled || nt < 8 || P < 1 || P > nt) return 0;  // rdy is indexed [panel * nt + tile row]: needs P <= nt
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int chunks = (P + 14) / 15;
+  std::vector<DfTask> tasks;
+  for (int c = 0; c < chunks; ++c) {
+    const int k0 = (int)((long long)P * c / chunks), k1 = (int)((long long)P * (c + 1) / chunks);
+    for (int i = 0; i < nt; ++i)
+      for (int j = 0; j <= i; ++j) tasks.push_back(DfTask{DF_UPD, i, j, k0 | (k1 << 16)});
+  }
+  AssemblyPlan* p = new AssemblyPlan;
+  p->n = n; p->m = m; p->nt = nt; p->ntasks = (int)tasks.size(); p->nsm = nsm;
+  p->flag_ints = 4 + 2 * (size_t)nt * nt;
+  cudaError_t e = cudaMalloc(&p->d_tasks, sizeof(int4) * tasks.size());
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_flags, sizeof(int) * p->flag_ints);
+  if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, sizeof(int) * p->flag_ints);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_tasks, tasks.data(), sizeof(int4) * tasks.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(p->d_tasks); cudaFree(p->d_flags);
+    delete p;
+    return (int)e;
+  }
+  *out = p;
+  return 0;
+}
+
+void dataflow_assembly_plan_destroy(AssemblyPlan* p) {
+  if (!p) return;
+  cudaFree(p->d_tasks); cudaFree(p->d_flags);
+  delete p;
+}
+
+// K (n x ldk, lower triangle, already holding Hx) -= MT * NB^T with NB = -MT diag(W).  Returns non-zero when the TMA
+// path is unavailable (the caller falls back to the SYRK kernel).
+int launch_assembly_dataflow(cudaStream_t st, const AssemblyPlan& p, double* K, int ldk, const double* MT,
+                             const double* NB, int ldmt) {
+  const size_t ntnt = (size_t)p.nt * p.nt;
+  cudaMemsetAsync(p.d_flags, 0, sizeof(int) * 2, st);                              // ticket, abort (sticky stays)
+  cudaMemsetAsync(p.d_flags + 4, 0x02, sizeof(int) * ntnt, st);                    // rdy: every panel "finished" (>= 2)
+  cudaMemsetAsync(p.d_flags + 4 + ntnt, 0, sizeof(int) * ntnt, st);                // cnt: no chunk applied yet
+  DfArgs a;
+  a.src = K; a.dst = K; a.W = nullptr; a.Dg = nullptr; a.Ginv = nullptr; a.tasks = p.d_tasks;
+  a.ticket = p.d_flags; a.abort = p.d_flags + 1; a.sticky = p.d_flags + 2; a.rdy = p.d_flags + 4; a.cnt = a.rdy + ntnt;
+  a.tlog = nullptr;
+  a.N = p.n; a.ld = ldk; a.nt = p.nt; a.ntasks = p.ntasks;
+  const int ctas = p.nsm < p.ntasks ? p.nsm : p.ntasks;
+  const int rc = dataflow_tma_launch_operands(st, &a, ctas, MT, p.n, ldmt, NB, p.n, ldmt);
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+int dataflow_assembly_abort_flag(cudaStream_t st, const AssemblyPlan& p, int* flag) {
+  cudaError_t e = cudaMemcpyAsync(flag, p.d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   return (int)e;
 }
 

@@ -669,6 +669,18 @@ static bool make_map(CUtensorMap* m, const double* base, int rows, int ld) {
 }
 #endif
 
+#if DF_TMA
+// Same kernel with the two UPD operands taken from arbitrary row-major matrices: C(i,j) -= A(i, k-range) B(j, k-range)^T.
+// Used for the condensed assembly M^T W M (A = MT, B = -MT diag(W)) as a list of UPD tasks with preset flags.
+static int df_kernel_launch_operands(cudaStream_t st, const DfArgs& a, int ctas, const double* A, int rowsA, int ldA,
+                                     const double* B, int rowsB, int ldB) {
+  CUtensorMap mapA, mapB;
+  if (!make_map(&mapA, A, rowsA, ldA) || !make_map(&mapB, B, rowsB, ldB)) return (int)cudaErrorNotSupported;
+  k_ldlt_dataflow<<<ctas, DF_THREADS, DF_SMEM, st>>>(a, mapA, mapB);
+  return 0;
+}
+#endif
+
 static int df_kernel_launch(cudaStream_t st, const DfArgs& a, int ctas, const double* W) {
 #if DF_TMA
   CUtensorMap mapA, mapB;

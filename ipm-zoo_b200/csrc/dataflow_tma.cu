@@ -12,4 +12,9 @@ int dataflow_tma_launch(cudaStream_t st, const void* args, int ctas, const doubl
   return df_kernel_launch(st, *static_cast<const DfArgs*>(args), ctas, W);
 }
 
+int dataflow_tma_launch_operands(cudaStream_t st, const void* args, int ctas, const double* A, int rowsA, int ldA,
+                                 const double* B, int rowsB, int ldB) {
+  return df_kernel_launch_operands(st, *static_cast<const DfArgs*>(args), ctas, A, rowsA, ldA, B, rowsB, ldB);
+}
+
 }  // namespace ipmz

@@ -36,7 +36,7 @@ void launch_refine_list(cudaStream_t st, const View& v, int nact, double thr, in
 void launch_assemble(cudaStream_t st, const View& v, int nslots);
 // out[r][c] = in[r][c] * d[c] (pre-scaled B operand MT diag(W) of the condensed assembly)
 void launch_scale_cols(cudaStream_t st, int nslots, const int* active, const double* in, double* out, int ld,
-                       size_t sM, int rows, int cols, const double* d, size_t sd);
+                       size_t sM, int rows, int cols, const double* d, size_t sd, double sign = 1.0);
 
 // ---- full_system.cu: the un-reduced Newton system in the FullLayout order ----
 void launch_assemble_full(cudaStream_t st, const View& v, int nslots);
@@ -86,6 +86,14 @@ int dataflow_abort_flag(cudaStream_t st, const DataflowPlan& p, int* flag);
 // one factorization with a per-task log: 4 x int64 per ticket (start ns, end ns, SM id, task words)
 int launch_ldlt_dataflow_logged(cudaStream_t st, DataflowPlan& p, const double* src, double* dst, double* Dg,
                                 double* Ginv, long long* host_log, int cap_tasks, int* ntasks);
+
+// condensed assembly K += MT diag(W) MT^T as UPD tasks of the dataflow kernel (one large QP, TMA build)
+struct AssemblyPlan;
+int dataflow_assembly_plan_create(AssemblyPlan** out, int n, int m);  // *out stays null when the path does not apply
+void dataflow_assembly_plan_destroy(AssemblyPlan* p);
+int launch_assembly_dataflow(cudaStream_t st, const AssemblyPlan& p, double* K, int ldk, const double* MT,
+                             const double* NB /* = -MT diag(W) */, int ldmt);
+int dataflow_assembly_abort_flag(cudaStream_t st, const AssemblyPlan& p, int* flag);
 
 struct FactorPlan {
   int N;        // matrix dimension

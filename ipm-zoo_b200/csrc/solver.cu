@@ -108,6 +108,7 @@ struct Workspace {
   TrsvWork tw{};
   LookAhead la{};
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
+  AssemblyPlan* asmp = nullptr;  // single large QP, NORMAL: condensed assembly as UPD tasks of the dataflow kernel
   int Naug = 0;
   int refine = 0;  // iterative-refinement steps of the normal reduction
   int refine_extra = 0;   // +1 on the late iterations of a single QP (run_ipm), see there
@@ -129,6 +130,7 @@ struct Workspace {
     cudaSetDevice(device);
     lookahead_destroy(&la);
     dataflow_plan_destroy(df);
+    dataflow_assembly_plan_destroy(asmp);
     for (void* p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -281,6 +283,10 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
     if (dataflow_min_n() > 0 && v.N >= dataflow_min_n()) {
       const int de = dataflow_plan_create(&w->df, v.N, v.ldk);
       if (de != 0) return fail(IPMZ_ERR_CUDA, std::string("dataflow_plan_create: ") + cudaGetErrorString((cudaError_t)de));
+      if (v.normal && s.m > 0) {
+        const int ae = dataflow_assembly_plan_create(&w->asmp, s.n, s.m);
+        if (ae != 0) return fail(IPMZ_ERR_CUDA, std::string("dataflow_assembly_plan_create: ") + cudaGetErrorString((cudaError_t)ae));
+      }
     }
   }
   CUDA_TRY(cudaEventCreate(&w->ev0));
@@ -348,6 +354,12 @@ static void assemble_and_factor(Workspace& w, const View& v, int nslots) {
     return;
   }
   launch_assemble(w.st, v, nslots);
+  if (v.normal && s.m > 0 && w.asmp && nslots == 1 && !v.active) {
+    // sign folded into the scaled operand: the UPD task subtracts
+    launch_scale_cols(w.st, 1, nullptr, v.MT, w.MTW, v.ldmt, v.sMT, s.n, s.m, v.W, s.ms, -1.0);
+    if (launch_assembly_dataflow(w.st, *w.asmp, v.K, v.ldk, v.MT, w.MTW, v.ldmt) == 0) return;
+    // TMA path unavailable: fall through to the SYRK kernel (which adds a positively scaled operand)
+  }
   if (v.normal && s.m > 0) {
     launch_scale_cols(w.st, nslots, v.active, v.MT, w.MTW, v.ldmt, v.sMT, s.n, s.m, v.W, s.ms);
     launch_syrk_ldl(w.st, nslots, v.active, v.K, v.K, v.ldk, v.sK, v.MT, v.ldmt, v.sMT, w.MTW, v.ldmt, v.sMT, s.n,
@@ -516,6 +528,11 @@ static int run_ipm(Workspace& w, double* ms_out) {
   CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
   if (ms_out) *ms_out = ms;
   w.tr_iters = it;
+  if (w.asmp) {
+    int aborted = 0;
+    CUDA_TRY((cudaError_t)dataflow_assembly_abort_flag(w.st, *w.asmp, &aborted));
+    if (aborted) return fail(IPMZ_ERR_CUDA, "condensed assembly on the dataflow kernel: a wait timed out");
+  }
   if (w.df) {
     int aborted = 0;
     CUDA_TRY((cudaError_t)dataflow_abort_flag(w.st, *w.df, &aborted));
