@@ -194,7 +194,11 @@ int dataflow_assembly_plan_create(AssemblyPlan** out, int n, int m) {
   int dev = 0, nsm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int chunks = (P + 14) / 15;
+  // chunks of the K range per tile: a task waits on at most 15 panels, which does not matter here (every flag is
+  // preset); fewer chunks = fewer C-tile reloads, more chunks = finer balance over the CTAs
+  int chunks = env_int("IPMZ_ASM_CHUNKS", (P + 14) / 15);
+  if (chunks < 1) chunks = 1;
+  if (chunks > P) chunks = P;
   std::vector<DfTask> tasks;
   for (int c = 0; c < chunks; ++c) {
     const int k0 = (int)((long long)P * c / chunks), k1 = (int)((long long)P * (c + 1) / chunks);
