@@ -199,6 +199,9 @@ int ipmz_factor_info(ipmz_factor_handle h, int* dataflow, int* ntasks, double* s
  * check that it is a topological order covering every tile exactly once (the invariant that makes
  * the device-side ticket queue deadlock-free).  counts3 = DIAG / TRSM / UPD tasks.  0 = valid. */
 int ipmz_schedule_check(int n, int workers, int* counts3, double* makespan_us, double* work_us);
+/* Host-only: the UPD task list of the condensed assembly M^T W M (n x n, inner dimension m) on the dataflow kernel
+ * covers every lower tile's K range exactly once and in order; *ntasks = 0 when that path does not apply. */
+int ipmz_assembly_schedule_check(int n, int m, int* ntasks);
 int ipmz_factor_get_solution(ipmz_factor_handle h, double* x_host);
 int ipmz_factor_get_ld(ipmz_factor_handle h, double* L_host, double* D_host);
 

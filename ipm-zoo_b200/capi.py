@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_symmetric_indefinite_factorization", "ipmz_overwriting_solve_bunch_kaufman", "ipmz_bk_factor_time",
     "ipmz_factor_create", "ipmz_factor_destroy", "ipmz_factor_set_matrix", "ipmz_factor_set_rhs",
     "ipmz_factor_run", "ipmz_factor_profile", "ipmz_factor_get_solution", "ipmz_factor_get_ld",
-    "ipmz_factor_info", "ipmz_schedule_check",
+    "ipmz_factor_info", "ipmz_schedule_check", "ipmz_assembly_schedule_check",
     "ipmz_batch_create", "ipmz_batch_destroy", "ipmz_batch_upload", "ipmz_batch_solve",
     "ipmz_batch_get_iterates", "ipmz_batch_get_x", "ipmz_batch_solve_group", "ipmz_batch_results",
 ]
@@ -447,6 +447,13 @@ def overwriting_solve_bunch_kaufman(LD, ipiv, b):
     _check(lib().ipmz_overwriting_solve_bunch_kaufman(LD.shape[0], _ptr(LD), ipiv.ctypes.data_as(C.POINTER(C.c_int)),
                                                      _ptr(b)))
     return b
+
+
+def assembly_schedule_check(n, m):
+    """(valid, ntasks) of the condensed-assembly task list (host only, no GPU needed)."""
+    nt = C.c_int()
+    rc = lib().ipmz_assembly_schedule_check(n, m, C.byref(nt))
+    return rc == 0, nt.value
 
 
 def overwriting_solve_ldlt(L, D, b):

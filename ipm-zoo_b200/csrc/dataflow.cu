@@ -199,12 +199,8 @@ int dataflow_assembly_plan_create(AssemblyPlan** out, int n, int m) {
   int chunks = env_int("IPMZ_ASM_CHUNKS", (P + 14) / 15);
   if (chunks < 1) chunks = 1;
   if (chunks > P) chunks = P;
-  std::vector<DfTask> tasks;
-  for (int c = 0; c < chunks; ++c) {
-    const int k0 = (int)((long long)P * c / chunks), k1 = (int)((long long)P * (c + 1) / chunks);
-    for (int i = 0; i < nt; ++i)
-      for (int j = 0; j <= i; ++j) tasks.push_back(DfTask{DF_UPD, i, j, k0 | (k1 << 16)});
-  }
+  const std::vector<DfTask> tasks = df_build_assembly_tasks(n, m, chunks);
+  if (!df_validate_assembly_tasks(n, m, tasks)) return (int)cudaErrorInvalidValue;
   AssemblyPlan* p = new AssemblyPlan;
   p->n = n; p->m = m; p->nt = nt; p->ntasks = (int)tasks.size(); p->nsm = nsm;
   p->flag_ints = 4 + 2 * (size_t)nt * nt;
@@ -219,6 +215,17 @@ int dataflow_assembly_plan_create(AssemblyPlan** out, int n, int m) {
   }
   *out = p;
   return 0;
+}
+
+// host only: the task list the assembly of an n x n condensed matrix with inner dimension m would run (0 tasks when
+// the path does not apply) and whether it covers every tile's K range exactly once in order
+bool dataflow_assembly_schedule_check(int n, int m, int* ntasks) {
+  const int nt = (n + DF_TILE - 1) / DF_TILE, P = (m + DF_TILE - 1) / DF_TILE;
+  if (ntasks) *ntasks = 0;
+  if (nt < 8 || P < 1 || P > nt) return true;  // not applicable: the SYRK kernel runs
+  const std::vector<DfTask> tasks = df_build_assembly_tasks(n, m, (P + 14) / 15);
+  if (ntasks) *ntasks = (int)tasks.size();
+  return df_validate_assembly_tasks(n, m, tasks);
 }
 
 void dataflow_assembly_plan_destroy(AssemblyPlan* p) {

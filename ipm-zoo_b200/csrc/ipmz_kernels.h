@@ -94,6 +94,7 @@ void dataflow_assembly_plan_destroy(AssemblyPlan* p);
 int launch_assembly_dataflow(cudaStream_t st, const AssemblyPlan& p, double* K, int ldk, const double* MT,
                              const double* NB /* = -MT diag(W) */, int ldmt);
 int dataflow_assembly_abort_flag(cudaStream_t st, const AssemblyPlan& p, int* flag);
+bool dataflow_assembly_schedule_check(int n, int m, int* ntasks);  // host only
 
 struct FactorPlan {
   int N;        // matrix dimension

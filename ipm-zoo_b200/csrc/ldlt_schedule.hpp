@@ -261,4 +261,40 @@ inline bool df_validate_schedule(int N, const DfSchedule& s) {
   return true;
 }
 
+// ---- condensed assembly as UPD tasks (dataflow.cu, launch_assembly_dataflow) -------------------------------------
+// Task list of K(i,j) -= A(i, :) B(j, :)^T over the lower-triangular tiles of an n x n matrix with an inner dimension
+// of m: the K range of every tile is cut into `chunks` consecutive pieces, emitted chunk-major so that the pieces of
+// one tile (ordered by the tile counter `cnt`) are thousands of tickets apart.
+inline std::vector<DfTask> df_build_assembly_tasks(int n, int m, int chunks) {
+  std::vector<DfTask> tasks;
+  const int nt = (n + DF_TILE - 1) / DF_TILE, P = (m + DF_TILE - 1) / DF_TILE;
+  if (nt <= 0 || P <= 0) return tasks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > P) chunks = P;
+  for (int c = 0; c < chunks; ++c) {
+    const int k0 = (int)((long long)P * c / chunks), k1 = (int)((long long)P * (c + 1) / chunks);
+    for (int i = 0; i < nt; ++i)
+      for (int j = 0; j <= i; ++j) tasks.push_back(DfTask{DF_UPD, i, j, k0 | (k1 << 16)});
+  }
+  return tasks;
+}
+
+// Every lower tile receives its K range [0, P) exactly once, in increasing order (the order the kernel's tile counter
+// enforces); P <= nt because the preset `rdy` flags are indexed [panel * nt + tile row].
+inline bool df_validate_assembly_tasks(int n, int m, const std::vector<DfTask>& tasks) {
+  const int nt = (n + DF_TILE - 1) / DF_TILE, P = (m + DF_TILE - 1) / DF_TILE;
+  if (P > nt) return false;
+  std::vector<int> cnt((size_t)nt * nt, 0);
+  for (const DfTask& tk : tasks) {
+    if ((tk.type & 0xff) != DF_UPD || tk.i < tk.j || tk.i >= nt || tk.j < 0) return false;
+    const int k0 = tk.k01 & 0xffff, k1 = tk.k01 >> 16;
+    if (k0 >= k1 || k1 > P || cnt[(size_t)tk.i * nt + tk.j] != k0) return false;
+    cnt[(size_t)tk.i * nt + tk.j] = k1;
+  }
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j)
+      if (cnt[(size_t)i * nt + j] != P) return false;
+  return true;
+}
+
 }  // namespace ipmz

@@ -245,6 +245,10 @@ int ipmz_schedule_check(int n, int workers, int* counts3, double* makespan_us, d
                                                                              : ipmz_fail(IPMZ_ERR_ARG, "invalid schedule");
 }
 
+int ipmz_assembly_schedule_check(int n, int m, int* ntasks) {
+  return dataflow_assembly_schedule_check(n, m, ntasks) ? IPMZ_OK : ipmz_fail(IPMZ_ERR_ARG, "invalid assembly task list");
+}
+
 int ipmz_debug_factor_timeline(ipmz_factor_handle h, double* out, int cap, int* nrec) {
   if (!h) return 1;
   if (ipmz_ensure_device(h->device)) return 2;

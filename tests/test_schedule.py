@@ -50,3 +50,15 @@ def test_random_sizes():
     rng = np.random.default_rng(0)
     for n in rng.integers(1, 6000, size=40):
         assert z.schedule_check(int(n), int(rng.integers(1, 200)))["valid"]
+
+
+@pytest.mark.parametrize("n,m,expect_tasks", [(8192, 4096, 3 * 2080), (2048, 1024, 136), (4096, 1, 528), (1024, 512, 36),
+                                              (1000, 2000, 0), (512, 256, 0), (8192, 8192, 5 * 2080), (3001, 777, 300)])
+def test_assembly_task_list_covers_every_tile_once(n, m, expect_tasks):
+    """Condensed assembly on the dataflow kernel (launch_assembly_dataflow): UPD-only task list, every lower tile's K
+    range [0, ceil(m/128)) applied exactly once and in order, at most 15 panels per task; not applicable (0 tasks,
+    the SYRK kernel runs) below 8 tile rows or when m > n."""
+    import ipm_zoo_b200 as z
+    ok, ntasks = z.assembly_schedule_check(n, m)
+    assert ok
+    assert ntasks == expect_tasks
