@@ -526,6 +526,17 @@ int launch_bk_factor(cudaStream_t st, int nslots, const int* active, double* S, 
   return (int)cudaGetLastError();
 }
 
+// Opt-in shared-memory sizes of the solve kernels; per device (called from factor_init, once for every device used).
+constexpr size_t BK_SOLVE_MAX_SMEM = 200 * 1024;  // x alone: n <= 25600
+int bk_init() {
+  constexpr int FAST_E = 8;
+  const size_t fast = (sizeof(double) * 3 + sizeof(int)) * (size_t)(FAST_E * BK_TPB);
+  cudaError_t e = cudaFuncSetAttribute(k_bk_solve_fast<FAST_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_bk_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SOLVE_MAX_SMEM);
+  return (int)e;
+}
+
 int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double* S, int ld, size_t sS, int n,
                     const int* ipiv, size_t sP, double* x, size_t sx) {
   if (n <= 0 || nslots <= 0) return 0;
@@ -533,24 +544,12 @@ int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double
   constexpr int FAST_E = 8;
   if (n <= FAST_E * BK_TPB) {  // latency-hidden variant: x, pivots and ipiv in shared memory, rows prefetched
     const size_t smem_fast = sizeof(double) * 3 * (size_t)n + sizeof(int) * (size_t)n;
-    static size_t opted_fast = 0;
-    if (smem_fast + 2048 > 48 * 1024 && smem_fast > opted_fast) {
-      const cudaError_t e =
-          cudaFuncSetAttribute(k_bk_solve_fast<FAST_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
-      if (e != cudaSuccess) return (int)e;
-      opted_fast = smem_fast;
-    }
     k_bk_solve_fast<FAST_E><<<dim3(1, nslots), BK_TPB, smem_fast, st>>>(a, x, sx);
     count_launch();
     return (int)cudaGetLastError();
   }
   const size_t smem = sizeof(double) * (size_t)n;
-  static size_t opted = 0;
-  if (smem + 1024 > 48 * 1024 && smem > opted) {  // static shared memory of the kernel counts against the 48 KB default
-    const cudaError_t e = cudaFuncSetAttribute(k_bk_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    opted = smem;
-  }
+  if (smem > BK_SOLVE_MAX_SMEM) return (int)cudaErrorInvalidValue;
   k_bk_solve<<<dim3(1, nslots), BK_TPB, smem, st>>>(a, x, sx);
   count_launch();
   return (int)cudaGetLastError();
@@ -613,9 +612,13 @@ int ipmz_bk_factor_time(int n, const double* A, int reps, double* ms_per_factori
   CUDA_TRY(cudaMalloc(&P.p, sizeof(int) * (size_t)n));
   CUDA_TRY(cudaMemset(S0.p, 0, bytes));
   CUDA_TRY(cudaMemcpy2D(S0.p, sizeof(double) * ld, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
+  struct Events {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  CUDA_TRY(cudaEventCreate(&ev.e0));
+  CUDA_TRY(cudaEventCreate(&ev.e1));
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
   double total = 0.0;
   for (int r = -1; r < reps; ++r) {  // r = -1: warm-up
     CUDA_TRY(cudaMemcpyAsync(S.p, S0.p, bytes, cudaMemcpyDeviceToDevice, nullptr));
@@ -627,8 +630,6 @@ int ipmz_bk_factor_time(int n, const double* A, int reps, double* ms_per_factori
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     if (r >= 0) total += ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *ms_per_factorization = total / reps;
   return IPMZ_OK;
 }

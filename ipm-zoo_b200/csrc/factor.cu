@@ -509,6 +509,8 @@ int factor_init() {
   if (e != cudaSuccess) return (int)e;
   const int te = trsv_init();
   if (te != 0) return te;
+  const int be = bk_init();
+  if (be != 0) return be;
   return dataflow_init();
 }
 

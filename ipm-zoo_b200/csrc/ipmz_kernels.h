@@ -48,6 +48,7 @@ void launch_full_unpack(cudaStream_t st, const View& v, int nslots, int mode);  
 // Both return a cudaError_t.
 int launch_bk_factor(cudaStream_t st, int nslots, const int* active, double* S, int ld, size_t sS, int n, int* ipiv,
                      size_t sP, int mirror_input);
+int bk_init();  // per-device opt-in shared-memory sizes of the solve kernels
 int launch_bk_solve(cudaStream_t st, int nslots, const int* active, const double* S, int ld, size_t sS, int n,
                     const int* ipiv, size_t sP, double* x, size_t sx);
 
