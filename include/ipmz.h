@@ -130,6 +130,9 @@ const char* ipmz_version(void);
 int ipmz_device_count(void);
 void ipmz_default_options(ipmz_options* opt);
 int ipmz_iterate_len(const ipmz_problem* p);
+/* Host-only: offsets of the unknown groups of the FULL reduction, dy dz dsl dsu dlam_y dlam_z dlam_l dlam_u ds dx dlam,
+ * followed by the system size N (12 ints; absent groups have zero width).  Only sizes and Settings of *p are read. */
+int ipmz_full_layout(const ipmz_problem* p, int* offsets12);
 /* Page-locked host buffers for the end-to-end path (H2D / D2H at full PCIe rate). */
 void* ipmz_host_alloc(size_t bytes);
 void ipmz_host_free(void* p);

@@ -12,7 +12,7 @@ EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE, EQ_REGULARIZATION = 0, 1, 2, 3  # ipmz_probl
 dp = C.POINTER(C.c_double)
 
 EXPORTED_SYMBOLS = [
-    "ipmz_last_error", "ipmz_version", "ipmz_device_count", "ipmz_default_options", "ipmz_iterate_len",
+    "ipmz_last_error", "ipmz_version", "ipmz_device_count", "ipmz_default_options", "ipmz_iterate_len", "ipmz_full_layout",
     "ipmz_host_alloc", "ipmz_host_free", "ipmz_launch_count", "ipmz_fp64_peak_probe",
     "ipmz_create", "ipmz_destroy", "ipmz_set_iterate", "ipmz_get_iterate", "ipmz_reset_iterate",
     "ipmz_solve", "ipmz_newton_step", "ipmz_get_trace", "ipmz_assemble", "ipmz_probe_kernels",
@@ -85,6 +85,8 @@ def lib():
         vp = C.c_void_p
         L.ipmz_default_options.argtypes = [C.POINTER(_Options)]
         L.ipmz_iterate_len.argtypes = [C.POINTER(_Problem)]
+        L.ipmz_full_layout.argtypes = [C.POINTER(_Problem), C.POINTER(C.c_int)]
+        L.ipmz_assembly_schedule_check.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.ipmz_create.argtypes = [C.POINTER(_Problem), C.POINTER(_Options), C.POINTER(vp)]
         L.ipmz_destroy.argtypes = [vp]
         L.ipmz_set_iterate.argtypes = [vp, dp]
@@ -447,6 +449,15 @@ def overwriting_solve_bunch_kaufman(LD, ipiv, b):
     _check(lib().ipmz_overwriting_solve_bunch_kaufman(LD.shape[0], _ptr(LD), ipiv.ctypes.data_as(C.POINTER(C.c_int)),
                                                      _ptr(b)))
     return b
+
+
+def full_layout(problem):
+    """Offsets of the FULL reduction's unknown groups (host only): dict name -> start, plus 'N'."""
+    ps = problem.c_struct()
+    o = (C.c_int * 12)()
+    _check(lib().ipmz_full_layout(C.byref(ps), o))
+    names = ("y", "z", "sl", "su", "ly", "lz", "ll", "lu", "s", "x", "lam", "N")
+    return dict(zip(names, list(o)))
 
 
 def assembly_schedule_check(n, m):

@@ -614,6 +614,19 @@ unsigned long long ipmz_launch_count(void) { return g_launch_count.load(); }
 
 int ipmz_iterate_len(const ipmz_problem* p) { return 5 * p->n + 6 * p->m_ineq + 6 * p->m_eq; }
 
+// Host only: where the unknowns of the FULL reduction sit (FullLayout, ipmz_device.cuh).  offsets12 = start of
+// dy dz dsl dsu dlam_y dlam_z dlam_l dlam_u ds dx dlam, then N; absent groups have zero width.
+int ipmz_full_layout(const ipmz_problem* p, int* offsets12) {
+  if (!p || !offsets12) return fail(IPMZ_ERR_ARG, "null argument");
+  if (p->n <= 0 || p->m_ineq < 0 || p->m_eq < 0) return fail(IPMZ_ERR_ARG, "bad sizes");
+  Shape s;
+  fill_shape(s, p);
+  const FullLayout f = full_layout(s);
+  const int o[12] = {f.oy, f.oz, f.osl, f.osu, f.oly, f.olz, f.oll, f.olu, f.os, f.ox, f.olam, f.N};
+  for (int i = 0; i < 12; ++i) offsets12[i] = o[i];
+  return IPMZ_OK;
+}
+
 // Copy between the caller's packed iterate(s) and the device packs. dir 0: host->device.
 static int move_iterates(Workspace& w, int mi_host, int me_host, double* packed, int dir) {
   const Shape& s = w.v.s;

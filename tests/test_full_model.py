@@ -56,3 +56,12 @@ def test_full_layout_size_matches_reference_count():
     assert fm.layout(p)["N"] == 5 * 200 + 6 * 100 == 1600
     q = CASES["ineq_only_30x12"]()
     assert fm.layout(q)["N"] == 30 + 6 * 12
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_library_full_layout_matches_the_model(name):
+    """The FullLayout the CUDA kernels index with (host function of ipmz_device.cuh, through the C ABI, no GPU) is
+    the layout of the numpy model for every Settings family of the golden cases."""
+    import ipm_zoo_b200 as z
+    p = CASES[name]()
+    assert z.full_layout(z.Problem.from_data(p)) == fm.layout(p)
