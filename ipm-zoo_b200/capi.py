@@ -195,7 +195,12 @@ class Problem:
 
     @property
     def N(self):
-        return self.n + self.m_ineq + self.m_eq
+        """Rows of the solved augmented steps the library writes (n + the constraint rows the Settings keep):
+        inequality rows count only when `ineq_bounds` is not NONE, equality rows only when `equalities` is set
+        (fill_shape in csrc/solver.cu)."""
+        mi = self.m_ineq if self.ineq_bounds != NONE else 0
+        me = self.m_eq if self.equalities else 0
+        return self.n + mi + me
 
     @property
     def iterate_len(self):

@@ -511,6 +511,8 @@ int factor_init() {
   if (te != 0) return te;
   const int be = bk_init();
   if (be != 0) return be;
+  const int fe = fused_batch_init();
+  if (fe != 0) return fe;
   return dataflow_init();
 }
 

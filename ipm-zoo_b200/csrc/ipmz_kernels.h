@@ -135,6 +135,12 @@ void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const doubl
                      size_t sC, const double* PA, int lda, size_t sA, const double* PB, int ldb, size_t sB, int rows,
                      int kdim, double sign);
 
+// ---- batch_fused.cu: the whole IPM solve of one small QP inside one persistent CTA, one launch per batch ----
+bool fused_batch_applicable(const View& v);  // AUGMENTED / NORMAL, LDL^T rows only, panel fits one CTA's shared memory
+int fused_batch_init();                      // per-device opt-in shared-memory size; returns cudaError_t
+// every problem 0..count-1 from its current iterate to convergence; refine_fixed < 0 = refinement by each problem's mu
+int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket);
+
 // ---- trsv.cu ----
 int trsv_init();  // opt-in shared memory size of the streaming solves
 void trsv_set_debug_log(long long* dev);  // debug: [2][nblk][8] timestamps of the next streaming solves

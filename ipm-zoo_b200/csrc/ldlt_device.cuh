@@ -69,7 +69,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // Each warp takes 16 x 16 output micro-tiles (4 DMMA accumulators).  LOWER: C is the lower
 // triangle of a square block (A and B index the same rows) and only tiles on/below the
 // diagonal are touched.
-template <bool LOWER>
+template <bool LOWER, int P = SP>
 __device__ __forceinline__ void smem_update(double* C, const double* A, const double* B, const double* d,
                                             int rows, int cols, int kb, int warp, int lane, int nwarps) {
   const int g = lane >> 2, q = lane & 3;
@@ -85,10 +85,10 @@ __device__ __forceinline__ void smem_update(double* C, const double* A, const do
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         const double dk = d[s * 4 + q];
-        af[s][0] = A[ra * SP + s * 4 + q];
-        af[s][1] = A[(ra + 8) * SP + s * 4 + q];
-        bf[s][0] = B[rb * SP + s * 4 + q] * dk;
-        bf[s][1] = B[(rb + 8) * SP + s * 4 + q] * dk;
+        af[s][0] = A[ra * P + s * 4 + q];
+        af[s][1] = A[(ra + 8) * P + s * 4 + q];
+        bf[s][0] = B[rb * P + s * 4 + q] * dk;
+        bf[s][1] = B[(rb + 8) * P + s * 4 + q] * dk;
       }
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
@@ -103,10 +103,10 @@ __device__ __forceinline__ void smem_update(double* C, const double* A, const do
       const bool kok = kk < kb;
       const double dk = kok ? d[kk] : 0.0;
       double af[2], bf[2];
-      af[0] = (kok && ra < rows) ? A[ra * SP + kk] : 0.0;
-      af[1] = (kok && ra + 8 < rows) ? A[(ra + 8) * SP + kk] : 0.0;
-      bf[0] = (kok && rb < cols) ? B[rb * SP + kk] * dk : 0.0;
-      bf[1] = (kok && rb + 8 < cols) ? B[(rb + 8) * SP + kk] * dk : 0.0;
+      af[0] = (kok && ra < rows) ? A[ra * P + kk] : 0.0;
+      af[1] = (kok && ra + 8 < rows) ? A[(ra + 8) * P + kk] : 0.0;
+      bf[0] = (kok && rb < cols) ? B[rb * P + kk] * dk : 0.0;
+      bf[1] = (kok && rb + 8 < cols) ? B[(rb + 8) * P + kk] * dk : 0.0;
       dmma884(acc[0][0], af[0], bf[0]);
       dmma884(acc[0][1], af[0], bf[1]);
       dmma884(acc[1][0], af[1], bf[0]);
@@ -118,8 +118,8 @@ __device__ __forceinline__ void smem_update(double* C, const double* A, const do
       for (int j = 0; j < 2; ++j) {
         const int row = mi * 16 + i * 8 + g, col = ni * 16 + j * 8 + 2 * q;
         if (row < rows) {
-          if (col < cols && (!LOWER || col <= row)) C[row * SP + col] -= acc[i][j][0];
-          if (col + 1 < cols && (!LOWER || col + 1 <= row)) C[row * SP + col + 1] -= acc[i][j][1];
+          if (col < cols && (!LOWER || col <= row)) C[row * P + col] -= acc[i][j][0];
+          if (col + 1 < cols && (!LOWER || col + 1 <= row)) C[row * P + col + 1] -= acc[i][j][1];
         }
       }
   }
@@ -139,11 +139,12 @@ constexpr int INV_SUB = 4 * INV_BLK; // per 32-wide sub-block
 // pipe:  X_b = R_b Binv_b^T  with  R_b = A_b - sum_{l<b} X_l D_l L_bl^T.
 constexpr int CBUF = 8 * SB;  // two 32 x 4 exchange buffers
 __device__ __forceinline__ double pivot_of(double d) { return d == 0.0 ? 1e-8 : d; }  // LinearSolvers.cpp:28
+template <int P = SP>
 __device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* dsm, double* dinv, double* colbuf,
                                             double* binv, int lane) {
   double a[SB];
 #pragma unroll
-  for (int c = 0; c < SB; ++c) a[c] = (lane < jb && c <= lane) ? S[(j0 + lane) * SP + j0 + c] : 0.0;
+  for (int c = 0; c < SB; ++c) a[c] = (lane < jb && c <= lane) ? S[(j0 + lane) * P + j0 + c] : 0.0;
   double* xbuf = colbuf;            // [32][4] current entries of the four columns
   double* wbuf = colbuf + 4 * SB;   // [32][4] the same after elimination inside the block (w = l d)
 #pragma unroll
@@ -199,12 +200,12 @@ __device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* d
   }
 #pragma unroll
   for (int c = 0; c < SB; ++c)
-    if (lane < jb && c < lane) S[(j0 + lane) * SP + j0 + c] = a[c];
+    if (lane < jb && c < lane) S[(j0 + lane) * P + j0 + c] = a[c];
   __syncwarp();
   // lane (b, j): column j of L_bb^-1 by forward substitution, scaled by D^-1
   {
     const int bb = lane >> 3, j = lane & 7;
-    const double* Lb = S + (j0 + 8 * bb) * SP + j0 + 8 * bb;
+    const double* Lb = S + (j0 + 8 * bb) * P + j0 + 8 * bb;
     double x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = (i == j) ? 1.0 : 0.0;
@@ -213,7 +214,7 @@ __device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* d
       double s = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (k < i) s += ((8 * bb + i < jb && k >= j) ? Lb[i * SP + k] : 0.0) * x[k];
+        if (k < i) s += ((8 * bb + i < jb && k >= j) ? Lb[i * P + k] : 0.0) * x[k];
       if (i > j) x[i] = -s;
     }
 #pragma unroll
@@ -228,12 +229,13 @@ __device__ __forceinline__ void warp_ldlt32(double* S, int j0, int jb, double* d
 // pipe.  L = the unit-lower 32 x 32 block at Lb (pitch SP), d its pivots, binv its four
 // D^-1 L^-1 blocks.  Each warp owns 16-row tiles and runs the four 8-column stages on them
 // without block-level synchronisation (rows are independent).
+template <int P = SP>
 __device__ __forceinline__ void panel_solve32(double* T, int nrows, const double* Lb, const double* d,
                                               const double* binv, int warp, int lane, int nwarps) {
   const int g = lane >> 2, q = lane & 3;
   for (int mt = warp; mt * 16 < nrows; mt += nwarps) {
-    double* T0 = T + (mt * 16 + g) * SP;
-    double* T1 = T0 + 8 * SP;
+    double* T0 = T + (mt * 16 + g) * P;
+    double* T1 = T0 + 8 * P;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       double acc0[2], acc1[2];
@@ -246,7 +248,7 @@ __device__ __forceinline__ void panel_solve32(double* T, int nrows, const double
           const int k = 4 * s + q;
           af0[s] = T0[k];
           af1[s] = T1[k];
-          bf[s] = -(Lb[(8 * b + g) * SP + k] * d[k]);
+          bf[s] = -(Lb[(8 * b + g) * P + k] * d[k]);
         }
 #pragma unroll
         for (int s = 0; s < 2 * b; ++s) {

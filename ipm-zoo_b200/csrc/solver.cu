@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -110,6 +111,8 @@ struct Workspace {
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
   AssemblyPlan* asmp = nullptr;  // single large QP, NORMAL: condensed assembly as UPD tasks of the dataflow kernel
   int Naug = 0;
+  bool fused = false;         // batch handles: the persistent one-CTA-per-problem kernel (batch_fused.cu)
+  int* fused_ticket = nullptr;
   int refine = 0;  // iterative-refinement steps of the normal reduction
   int refine_extra = 0;   // +1 on the late iterations of a single QP (run_ipm), see there
   bool refine_auto = false;
@@ -230,7 +233,8 @@ static int upload_data(Workspace& w, const ipmz_problem* p) {
   return IPMZ_OK;
 }
 
-static int create_workspace(Workspace** out, int count, const ipmz_problem* p, const ipmz_options* opt_in) {
+static int create_workspace(Workspace** out, int count, const ipmz_problem* p, const ipmz_options* opt_in,
+                            bool batch_handle = false) {
   int rc = check_problem(p);
   if (rc) return rc;
   if (count <= 0) return fail(IPMZ_ERR_ARG, "count must be positive");
@@ -310,10 +314,15 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (s.hard_eq) ALLOC(w->ipiv, C * v.ldk);
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
+  ALLOC(w->fused_ticket, 1);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
 #undef ALLOC
   v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
   v.active = nullptr;
+  {
+    const char* e = getenv("IPMZ_BATCH_FUSED");
+    w->fused = batch_handle && fused_batch_applicable(v) && !(e && atoi(e) == 0);
+  }
   if (!w->sc_host.resize(count)) return fail(IPMZ_ERR_ALLOC, "cudaHostAlloc of the Scal mirror failed");
   w->active_host.resize(count);
 
@@ -481,6 +490,22 @@ static int run_ipm(Workspace& w, double* ms_out) {
   for (int i = 0; i < count; ++i) w.active_host[i] = i;
   bool identity = true;
   CUDA_TRY(cudaEventRecord(w.ev0, w.st));
+  if (w.fused) {
+    // one launch: every problem runs its whole predictor-corrector loop inside a persistent CTA; the host reads the
+    // per-problem records once, at the end
+    v.active = nullptr;
+    const int e = launch_ipm_batch(w.st, v, count, w.refine_auto ? -1 : w.refine, w.fused_ticket);
+    if (e != 0) return fail(IPMZ_ERR_CUDA, std::string("launch_ipm_batch: ") + cudaGetErrorString((cudaError_t)e));
+    CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal) * count, cudaMemcpyDeviceToHost, w.st));
+    CUDA_TRY(cudaEventRecord(w.ev1, w.st));
+    CUDA_TRY(cudaEventSynchronize(w.ev1));
+    CUDA_TRY(cudaGetLastError());
+    float fms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&fms, w.ev0, w.ev1));
+    if (ms_out) *ms_out = fms;
+    w.tr_iters = 0;
+    return IPMZ_OK;
+  }
   int it = 0;
   for (;; ++it) {
     v.active = identity ? nullptr : w.active_dev;
@@ -875,7 +900,7 @@ int ipmz_probe_kernels(ipmz_handle h, int reps, double* ms_per_launch, double* b
 int ipmz_batch_create(int count, const ipmz_problem* p, const ipmz_options* opt, ipmz_batch_handle* out) {
   if (!out) return fail(IPMZ_ERR_ARG, "null out handle");
   Workspace* w = nullptr;
-  const int rc = create_workspace(&w, count, p, opt);
+  const int rc = create_workspace(&w, count, p, opt, true);
   if (rc) return rc;
   *out = new ipmz_batch_s{w, p->m_ineq, p->m_eq, 0.0};
   return IPMZ_OK;

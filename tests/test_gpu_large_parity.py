@@ -1,0 +1,168 @@
+"""Oracle-anchored parity at BASELINE.json's full sizes (cfg2 n=2048, cfg3 n=8192, cfg5 n=4096).
+
+The goldens are committed by tests/golden/make_golden_large.py:
+  cfg2  the UNMODIFIED reference's whole solve (oracle/_ref), asserted bit-for-bit equal to the port at N = 3072,
+        plus step records (start iterate, both Newton steps, alpha_aff / sigma / alpha, iterate after the update)
+        at iterations 0, 3, last-2 and last-1;
+  cfg3  the port's first iteration at N = 12288 (one LDL^T = 10 CPU-minutes);
+  cfg5  the port's solve for eps = 1e-6 and 1e-10 and step records of the last three iterations (mu <~ 1e-6).
+Each test uploads the oracle's iterate, runs ONE iteration of the CUDA path (ipmz_newton_step) and compares step for
+step -- so the dataflow LDL^T, the streaming solves, the TMA condensed assembly and the refinement policy are checked
+against the oracle where they run, not against each other.
+
+Tolerances (north_star): Newton step 1e-9 relative (norm-wise, max|d - d_ref| / max|d_ref|), same iteration count,
+final objective within 1e-8.  The one documented exception: cfg5's last iterations, where cond(K) ~ 1/mu ~ 1e8-1e9
+bounds the agreement of ANY two FP64 factorizations at cond * eps ~ 1e-7 ("hard parts"); there the
+bound is CFG5_LATE_TOL and the measured errors are written to gpurun_out/parity_large.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import problems as P
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+STEP_TOL = 1e-9
+CFG5_LATE_TOL = 1e-6
+MEASURED = {}
+
+
+@pytest.fixture(scope="module")
+def z():
+    import ipm_zoo_b200 as z
+    assert z.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return z
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def record(key, **vals):
+    MEASURED[key] = {k: float(v) for k, v in vals.items()}
+    out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_large.json"), "w") as f:
+            json.dump(MEASURED, f, indent=1, sort_keys=True)
+
+
+def check_step(s, g, pre, key, tol=STEP_TOL, reset=False):
+    """One iteration of the CUDA path from the golden's start iterate against the golden's record."""
+    if reset:
+        s.reset_iterate()
+    else:
+        s.set_iterate(g[pre + "start"])
+    sa, sc, aa, sg, al = s.newton_step()
+    ea, ec = relerr(sa, g[pre + "step_aff"]), relerr(sc, g[pre + "step_cor"])
+    record(key, step_aff=ea, step_cor=ec, alpha_aff=abs(aa - g[pre + "alpha_aff"]), sigma=abs(sg - g[pre + "sigma"]),
+           alpha=abs(al - g[pre + "alpha"]), mu=g[pre + "mu"])
+    assert ea < tol, "affine step %s: %.3e" % (key, ea)
+    assert ec < tol, "corrector step %s: %.3e" % (key, ec)
+    scale = max(tol / STEP_TOL, 1.0)
+    assert abs(aa - g[pre + "alpha_aff"]) < 1e-9 * scale * max(1.0, abs(g[pre + "alpha_aff"]))
+    assert abs(sg - g[pre + "sigma"]) < 1e-8 * scale
+    assert abs(al - g[pre + "alpha"]) < 1e-9 * scale * max(1.0, abs(g[pre + "alpha"]))
+
+
+def check_traces(tr, g, k, key):
+    """f / res / mu of every iteration against the oracle's trace (the trajectories share every Newton step to 1e-9)."""
+    f, res, mu = (np.asarray(tr[a][:k + 1]) for a in ("f", "res", "mu"))
+    ef = float(np.max(np.abs(f - g["f"]) / np.maximum(1.0, np.abs(g["f"]))))
+    er = float(np.max(np.abs(res - g["res"]) / np.maximum(np.abs(g["res"]), 1e-12)))
+    em = float(np.max(np.abs(mu - g["mu"]) / np.maximum(np.abs(g["mu"]), 1e-12)))
+    record(key, f=ef, res_rel=er, mu_rel=em)
+    assert ef < 1e-8
+    assert er < 1e-3 and em < 1e-3
+
+
+@pytest.mark.parametrize("red", ["AUGMENTED", "NORMAL", "FULL"])
+def test_cfg2_reference_golden_steps_and_solve(z, red):
+    g = np.load(os.path.join(GOLD, "cfg2_ineq_box_2048x1024.npz"))
+    p = P.ineq_box(2048, 1024, 2, kind="shift")
+    assert abs(ol_checksum(p) - float(g["checksum"])) < 1e-9 * float(g["checksum"])
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=getattr(z, red)))
+    for it in g["step_iters"]:
+        check_step(s, g, "it%d_" % it, "cfg2_%s_it%d" % (red, it), reset=(it == 0))
+    s.reset_iterate()
+    r = s.solve()
+    k = int(g["iterations"])
+    assert r.iterations == k and r.converged == bool(g["converged"])
+    assert abs(r.f - g["f"][k]) <= 1e-8 * max(1.0, abs(g["f"][k]))
+    check_traces(s.trace(k), g, k, "cfg2_%s_trace" % red)
+    x = s.iterate()
+    assert np.max(np.abs(x[:p.n] - g["iterate"][:p.n])) < 1e-7
+    s.close()
+
+
+def ol_checksum(p):
+    parts = [p.Q, p.c, p.A, p.l_A, p.u_A, p.C, p.d, p.l_x, p.u_x]
+    return float(sum(np.sum(np.abs(a)) for a in parts if a is not None))
+
+
+@pytest.mark.parametrize("red", ["NORMAL", "AUGMENTED"])
+def test_cfg3_first_iteration_vs_oracle(z, red):
+    """N = 12288 augmented / 8192 condensed: the dataflow LDL^T, the TMA condensed assembly and the streaming solves
+    against the oracle's first iteration, then the iterate after that iteration (max_iter = 1)."""
+    g = np.load(os.path.join(GOLD, "cfg3_first_iteration_8192x4096.npz"))
+    p = P.ineq_box(8192, 4096, 3, kind="shift")
+    assert abs(ol_checksum(p) - float(g["checksum"])) < 1e-9 * float(g["checksum"])
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=getattr(z, red), max_iter=1))
+    sa, sc, aa, sg, al = s.newton_step()
+    ea, ec = relerr(sa, g["it0_step_aff"]), relerr(sc, g["it0_step_cor"])
+    record("cfg3_%s_it0" % red, step_aff=ea, step_cor=ec, alpha=abs(al - g["it0_alpha"]))
+    assert ea < STEP_TOL and ec < STEP_TOL
+    assert abs(aa - g["it0_alpha_aff"]) < 1e-9 and abs(sg - g["it0_sigma"]) < 1e-8 and abs(al - g["it0_alpha"]) < 1e-9
+    r = s.solve()
+    assert r.iterations == 1 and not r.converged
+    tr = s.trace(1)
+    assert abs(tr["f"][0] - g["it0_f"]) <= 1e-8 * max(1.0, abs(g["it0_f"]))
+    assert abs(tr["res"][0] - g["it0_res"]) <= 1e-9 * g["it0_res"]
+    assert abs(tr["f"][1] - g["it0_f1"]) <= 1e-8 * max(1.0, abs(g["it0_f1"]))
+    assert abs(tr["res"][1] - g["it0_res1"]) <= 1e-8 * g["it0_res1"]
+    assert abs(tr["mu"][1] - g["it0_mu1"]) <= 1e-8 * g["it0_mu1"]
+    it = s.iterate()
+    assert relerr(it, g["it0_after"]) < 1e-9
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_late", "cfg3_late"])
+@pytest.mark.parametrize("red", ["NORMAL", "AUGMENTED"])
+def test_late_iteration_vs_oracle(z, name, red):
+    """A late iterate (mu <~ 1e-6, where the NORMAL reduction takes its refinement steps) dumped once by the CUDA path
+    and handed to the port (make_golden_large.py late): one iteration from it, step for step."""
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(name + ".npz not generated")
+    g = np.load(path)
+    p = P.ineq_box(2048, 1024, 2, kind="shift") if name.startswith("cfg2") else P.ineq_box(8192, 4096, 3, kind="shift")
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=getattr(z, red)))
+    check_step(s, g, "late_", "%s_%s" % (name, red))
+    s.close()
+
+
+@pytest.mark.parametrize("eps", ["1em06", "1em10"])
+@pytest.mark.parametrize("red", ["AUGMENTED", "NORMAL"])
+def test_cfg5_last_iterations_and_solve(z, eps, red):
+    g = np.load(os.path.join(GOLD, "cfg5_portfolio_4096_eps%s_steps.npz" % eps))
+    p = P.portfolio(4096, 32, {"1em06": 1e-6, "1em10": 1e-10}[eps], 5)
+    assert abs(ol_checksum(p) - float(g["checksum"])) < 1e-9 * float(g["checksum"])
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=getattr(z, red)))
+    for it in g["step_iters"]:
+        check_step(s, g, "it%d_" % it, "cfg5_%s_%s_it%d" % (eps, red, it), tol=CFG5_LATE_TOL)
+    s.reset_iterate()
+    r = s.solve()
+    k = int(g["iterations"])
+    assert r.converged and bool(g["converged"])
+    assert r.iterations == k
+    assert abs(r.f - g["f"][k]) <= 1e-8 * max(1.0, abs(g["f"][k]))
+    tr = s.trace(k)
+    assert np.max(np.abs(np.asarray(tr["f"][:k + 1]) - g["f"]) / np.maximum(1.0, np.abs(g["f"]))) < 1e-8
+    x = s.iterate()[:p.n]
+    assert np.max(np.abs(x - g["x"])) < 1e-7
+    assert abs(x.sum() - 1.0) < 1e-7 and x.min() > -1e-9
+    s.close()
