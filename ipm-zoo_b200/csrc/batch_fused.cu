@@ -29,6 +29,7 @@
 //   solves             forward / pivots / backward with x in shared memory, 64-row blocks
 //   back-substitution  eliminated Delta's, ratio test, centring parameter, corrector right-hand side, update
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "ipmz_device.cuh"
 #include "ipmz_kernels.h"
@@ -37,7 +38,22 @@
 
 namespace ipmz {
 
+// debug builds (-DIPMZ_FUSED_CLOCKS): SM cycles per phase, summed over every CTA's thread 0
+__device__ unsigned long long g_fused_clk[16];
+
 namespace {
+
+#ifdef IPMZ_FUSED_CLOCKS
+#define FPH(i) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&g_fused_clk[i], (unsigned long long)(t__ - ph_last)); ph_last = t__; } } while (0)
+#define FPH_DECL long long ph_last = clock64()
+#define FSUB_BEGIN long long sub_t0__ = clock64()
+#define FSUB_END(i) do { __syncthreads(); if (threadIdx.x == 0) atomicAdd(&g_fused_clk[i], (unsigned long long)(clock64() - sub_t0__)); } while (0)
+#else
+#define FPH(i) do {} while (0)
+#define FPH_DECL do {} while (0)
+#define FSUB_BEGIN do {} while (0)
+#define FSUB_END(i) do {} while (0)
+#endif
 
 constexpr int FT = 256;          // threads per CTA
 constexpr int FW = FT / 32;      // warps
@@ -53,6 +69,7 @@ struct FusedArgs {
   int* ticket;
   int refine_fixed;  // >= 0: that many refinement steps per condensed solve; -1: by the problem's mu (solver.cu policy)
   int smem_doubles;
+  int dbg;  // experiments (IPMZ_FUSED_DBG): 1 = only the opening matvecs (30x), 2 = assembly (20x), 3 = + LDL^T, 4 = + one solve
 };
 
 __device__ __forceinline__ double wsum(double v) {
@@ -481,7 +498,11 @@ __device__ void condensed_solve(const View& v, int p, const double* rvec, int ac
   }
   for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, rvec, 1);
   __syncthreads();
-  ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sol, sm);
+  {
+    FSUB_BEGIN;
+    ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sol, sm);
+    FSUB_END(8);
+  }
   if (s.m > 0) {
     cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, sol, v.Mx + (size_t)p * s.ms);
     __syncthreads();
@@ -548,6 +569,33 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
       sc.iters = 0; sc.done = 0; sc.mu_c = 0.0; sc.alpha = 0.0; sc.alpha_aff = 0.0; sc.sigma = 0.0;
     }
     double* V = v.V + (size_t)p * v.sp;
+    if (a.dbg == 1) {
+      for (int rep = 0; rep < 30; ++rep) {
+        cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+        cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
+        cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
+      }
+      __syncthreads();
+      continue;
+    }
+    if (a.dbg >= 2) {
+      cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+      cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
+      __syncthreads();
+      {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = tid; i < len; i += FT) residuals_rhs_body<0>(v, p, i, acc);
+        __syncthreads();
+      }
+      for (int rep = 0; rep < 20; ++rep) {
+        assemble_normal(v, p, sm);
+        if (a.dbg >= 3) ldlt_panels(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sm);
+        if (a.dbg >= 4) ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, v.sol + (size_t)p * v.ssol, sm);
+      }
+      __syncthreads();
+      continue;
+    }
+    FPH_DECL;
     for (;;) {
       // ---- Q x, M x, M^T lambda
       cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
@@ -556,6 +604,7 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
         cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
       }
       __syncthreads();
+      FPH(0);
       // ---- residuals, W, objective / res / mu, stopping test, predictor right-hand side
       {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -565,15 +614,19 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
         if (tid == 0) residuals_finish(v, p, tot);
         __syncthreads();
       }
+      FPH(1);
       if (sc.done != 0) break;
       int nref = 0;
       if (v.normal) nref = a.refine_fixed >= 0 ? a.refine_fixed : ((s.reg_eq || sc.mu < 1e-3) ? 1 : 0);
       // ---- assembly + factorization
       if (v.normal && s.m > 0) assemble_normal(v, p, sm);
       else assemble_augmented(v, p);
+      FPH(2);
       ldlt_panels(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sm);
+      FPH(3);
       // ---- predictor
       newton_direction<0>(v, p, nref, red, sm);
+      FPH(4);
       {
         double m1[1] = {0.0};
         for (int i = tid; i < len; i += FT) mu_affine_body(v, p, i, m1[0]);
@@ -588,7 +641,9 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
         for (int i = tid; i < len; i += FT) residuals_rhs_body<1>(v, p, i, acc);
         __syncthreads();
       }
+      FPH(5);
       newton_direction<1>(v, p, nref, red, sm);
+      FPH(6);
       // ---- v += 0.995 alpha dv (Optimizer.cpp:216-238)
       {
         const double st = v.ftb * sc.alpha;
@@ -597,6 +652,7 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
         __syncthreads();
         if (tid == 0) sc.iters += 1;
       }
+      FPH(7);
     }
     __syncthreads();
   }
@@ -624,6 +680,14 @@ bool fused_batch_applicable(const View& v) {
   return (size_t)fused_smem_doubles(v) * sizeof(double) <= 200 * 1024;
 }
 
+// debug: read and clear the per-phase cycle counters (zeros unless built with -DIPMZ_FUSED_CLOCKS)
+int fused_read_clocks(unsigned long long* out16) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_fused_clk, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return (int)e;
+  unsigned long long z[16] = {0};
+  return (int)cudaMemcpyToSymbol(g_fused_clk, z, sizeof(z));
+}
+
 int fused_batch_init() {
   return (int)cudaFuncSetAttribute(k_ipm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
@@ -638,6 +702,7 @@ int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed
   a.ticket = ticket;
   a.refine_fixed = refine_fixed;
   a.smem_doubles = fused_smem_doubles(v);
+  a.dbg = getenv("IPMZ_FUSED_DBG") ? atoi(getenv("IPMZ_FUSED_DBG")) : 0;
   const size_t smem = (size_t)a.smem_doubles * sizeof(double);
   cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
@@ -647,6 +712,10 @@ int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ipm_batch, FT, smem);
   if (e != cudaSuccess) return (int)e;
   if (per_sm < 1) per_sm = 1;
+  if (const char* e = getenv("IPMZ_FUSED_CTAS_PER_SM")) {  // experiments: fewer problems in flight = smaller L2 footprint
+    const int want = atoi(e);
+    if (want >= 1 && want < per_sm) per_sm = want;
+  }
   int grid = nsm * per_sm;
   if (grid > count) grid = count;
   k_ipm_batch<<<grid, FT, smem, st>>>(a);

@@ -140,6 +140,7 @@ bool fused_batch_applicable(const View& v);  // AUGMENTED / NORMAL, LDL^T rows o
 int fused_batch_init();                      // per-device opt-in shared-memory size; returns cudaError_t
 // every problem 0..count-1 from its current iterate to convergence; refine_fixed < 0 = refinement by each problem's mu
 int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket);
+int fused_read_clocks(unsigned long long* out16);  // debug builds (-DIPMZ_FUSED_CLOCKS)
 
 // ---- trsv.cu ----
 int trsv_init();  // opt-in shared memory size of the streaming solves

@@ -896,6 +896,13 @@ int ipmz_probe_kernels(ipmz_handle h, int reps, double* ms_per_launch, double* b
   return IPMZ_OK;
 }
 
+// debug (library built with -DIPMZ_FUSED_CLOCKS): SM cycles per phase of the persistent batch kernel since the last call
+int ipmz_debug_fused_clocks(unsigned long long* out16) {
+  if (!out16) return fail(IPMZ_ERR_ARG, "null argument");
+  CUDA_TRY((cudaError_t)fused_read_clocks(out16));
+  return IPMZ_OK;
+}
+
 // ---- batch ------------------------------------------------------------------------------
 int ipmz_batch_create(int count, const ipmz_problem* p, const ipmz_options* opt, ipmz_batch_handle* out) {
   if (!out) return fail(IPMZ_ERR_ARG, "null out handle");

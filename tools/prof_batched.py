@@ -23,3 +23,13 @@ for rep in range(2):
     res, ms = bs.solve(per_problem=False)
     print("batch %d: device %.2f ms, wall %.2f ms -> %.0f solves/s" % (cnt, ms, (time.perf_counter() - t0) * 1e3, cnt / ms * 1e3))
 bs.close()
+import ctypes as C
+clk = (C.c_ulonglong * 16)()
+if hasattr(z.lib(), "ipmz_debug_fused_clocks") and z.lib().ipmz_debug_fused_clocks(clk) == 0 and sum(clk) > 0:
+    names = ["matvecs", "residuals", "assembly", "ldlt", "predictor", "mu+rhs", "corrector", "update"]
+    tot = float(sum(clk))
+    if clk[12]:
+        print("  matvec per chunk (cycles): wait %.0f compute %.0f sync+issue %.0f over %d chunks" % (clk[9] / clk[12], clk[10] / clk[12], clk[11] / clk[12], clk[12]))
+    tot = float(sum(clk[:8])) or 1.0
+    print("phase clocks (both reps): " + ", ".join("%s %.1f%%" % (names[i], 100.0 * clk[i] / tot) for i in range(8)))
+    print("  inside predictor/corrector: " + ", ".join("sub%d %.1f%%" % (i, 100.0 * clk[i] / tot) for i in range(8, 16) if clk[i]))
