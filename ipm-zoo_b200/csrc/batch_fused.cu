@@ -145,6 +145,84 @@ __device__ __forceinline__ void cta_matvec(const double* __restrict__ A, int lda
   }
 }
 
+// Matrix-vector product, TMA version (default; -DIPMZ_FUSED_NO_TMA_MV selects cta_matvec above): the matrix (rows contiguous, pitch lda) streams through
+// two 32 KB shared-memory buffers by bulk copies (cp.async.bulk.shared.global, SASS UBLKCP): ONE instruction of one
+// thread moves a whole chunk and completes on an mbarrier by transaction bytes.  Work split inside a chunk: S = 2^k
+// lanes share one row (S >= cols / 16, so a lane's part of x is 8 double2 registers loaded once per call), FT / S rows
+// per chunk; lane `seg` of a row takes the column pairs seg + S j (conflict-free reads, 8 independent 16-byte loads in
+// flight per thread) and a row is finished by log2(S) shuffle steps.
+constexpr int MV_NBUF = 2;
+constexpr int MV_CHUNK = 4096;  // doubles per staging buffer
+__shared__ __align__(8) unsigned long long g_mvbar[MV_NBUF];  // one mbarrier per staging buffer, initialised by the kernel
+__shared__ unsigned g_mvph;                                    // their phase bits (uniform per CTA)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned da = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  // earlier generic-proxy accesses of the buffer (other phases use the same shared memory) before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(da), "l"(gsrc), "r"(bytes), "r"(ba) : "memory");
+}
+// bar: MV_NBUF mbarriers (count 1) initialised once per kernel; ph: their phase bits, carried by the caller
+__device__ __noinline__ void cta_matvec_tma(const double* __restrict__ A, int lda, int rows, int cols, const double* x,
+                                            double* y, double* sm) {
+  const int tid = threadIdx.x;
+  unsigned long long* bar = g_mvbar;
+  const int c2 = (cols + 1) >> 1;
+  int S = 4;
+  while (8 * S < c2) S <<= 1;  // cols <= 512 -> S <= 32
+  int R = FT / S;              // rows per chunk
+  if (R * lda > MV_CHUNK) R = MV_CHUNK / lda;
+  const int nch = (rows + R - 1) / R;
+  const int rr = tid / S, seg = tid - rr * S;
+  __syncthreads();  // the staging buffers are free and x is visible
+  unsigned ph = g_mvph;
+  if (tid == 0)
+    for (int c = 0; c < MV_NBUF && c < nch; ++c)
+      bulk_load(sm + c * MV_CHUNK, A + (size_t)c * R * lda, (unsigned)(min(R, rows - c * R) * lda) * 8u, bar + c);
+  double2 xr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = seg + S * j;
+    xr[j] = k < c2 ? reinterpret_cast<const double2*>(x)[k] : make_double2(0.0, 0.0);
+  }
+  for (int c = 0; c < nch; ++c) {
+    const int bi = c % MV_NBUF;
+    mbar_wait(bar + bi, (ph >> bi) & 1u);
+    ph ^= 1u << bi;
+    const int r0 = c * R, nr = min(R, rows - r0);
+    {
+      const double2* a2 = reinterpret_cast<const double2*>(sm + bi * MV_CHUNK + (size_t)(rr < nr ? rr : 0) * lda);
+      double2 av[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = seg + S * j;
+        av[j] = k < c2 ? a2[k] : make_double2(0.0, 0.0);
+      }
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        acc0 = fma(av[j].x, xr[j].x, acc0); acc1 = fma(av[j].y, xr[j].y, acc1);
+        acc2 = fma(av[j + 1].x, xr[j + 1].x, acc2); acc3 = fma(av[j + 1].y, xr[j + 1].y, acc3);
+      }
+      double t = (acc0 + acc1) + (acc2 + acc3);
+      for (int o = S >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (seg == 0 && rr < nr) y[r0 + rr] = t;
+    }
+    __syncthreads();
+    if (tid == 0 && c + MV_NBUF < nch)
+      bulk_load(sm + bi * MV_CHUNK, A + (size_t)(c + MV_NBUF) * R * lda,
+                (unsigned)(min(R, rows - (c + MV_NBUF) * R) * lda) * 8u, bar + bi);
+  }
+  if (tid == 0) g_mvph = ph;  // read by the next call after its opening barrier
+}
+#ifndef IPMZ_FUSED_NO_TMA_MV
+#define MATVEC(A_, lda_, rows_, cols_, x_, y_) cta_matvec_tma(A_, lda_, rows_, cols_, x_, y_, sm)
+#else
+#define MATVEC(A_, lda_, rows_, cols_, x_, y_) cta_matvec(A_, lda_, rows_, cols_, x_, y_)
+#endif
+
 // ---- assembly ---------------------------------------------------------------------------------------------------
 // NORMAL: K(lower) = Q + diag(hd) + MT diag(w) MT^T, hd = Y^-1 L_y + Z^-1 L_z.  sm: FSTAGES stages | w[ms] | hd[ns].
 __device__ void assemble_normal(const View& v, int p, double* sm) {
@@ -493,7 +571,7 @@ __device__ void condensed_solve(const View& v, int p, const double* rvec, int ac
   if (s.m > 0) {
     for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, rvec, 0);
     __syncthreads();
-    cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, v.tm + (size_t)p * s.ms, v.tn + (size_t)p * s.ns);
+    MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, v.tm + (size_t)p * s.ms, v.tn + (size_t)p * s.ns);
     __syncthreads();
   }
   for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, rvec, 1);
@@ -504,7 +582,7 @@ __device__ void condensed_solve(const View& v, int p, const double* rvec, int ac
     FSUB_END(8);
   }
   if (s.m > 0) {
-    cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, sol, v.Mx + (size_t)p * s.ms);
+    MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, sol, v.Mx + (size_t)p * s.ms);
     __syncthreads();
   }
   for (int i = tid; i < len; i += FT) recover_dual_body(v, p, i, rvec, accumulate);
@@ -526,11 +604,11 @@ __device__ void newton_direction(const View& v, int p, int nref, double (*red)[F
     condensed_solve(v, p, v.rhs, 0, sm);
     double* out = v.out + (size_t)p * (s.ns + s.ms);
     for (int r = 0; r < nref; ++r) {
-      cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, out, v.Qd + (size_t)p * s.ns);
+      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, out, v.Qd + (size_t)p * s.ns);
       if (s.m > 0) {
-        cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, out + s.ns, v.tn + (size_t)p * s.ns);
+        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, out + s.ns, v.tn + (size_t)p * s.ns);
         // first refinement step: out's dx is still the vector the condensed solve just multiplied by M (Mx)
-        if (r > 0) cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, out, v.Mx + (size_t)p * s.ms);
+        if (r > 0) MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, out, v.Mx + (size_t)p * s.ms);
       }
       __syncthreads();
       for (int i = tid; i < len; i += FT) aug_residual_body(v, p, i);
@@ -554,6 +632,12 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[4][FW];
   __shared__ int s_p;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MV_NBUF; ++i) mbar_init(g_mvbar + i, 1);
+    g_mvph = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
   const View& v = a.v;
   const Shape& s = v.s;
   const int tid = threadIdx.x;
@@ -569,18 +653,19 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
       sc.iters = 0; sc.done = 0; sc.mu_c = 0.0; sc.alpha = 0.0; sc.alpha_aff = 0.0; sc.sigma = 0.0;
     }
     double* V = v.V + (size_t)p * v.sp;
+#ifdef IPMZ_FUSED_DBG_MODES
     if (a.dbg == 1) {
       for (int rep = 0; rep < 30; ++rep) {
-        cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
-        cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
-        cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
+        MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+        MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
+        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
       }
       __syncthreads();
       continue;
     }
     if (a.dbg >= 2) {
-      cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
-      cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
+      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+      MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
       __syncthreads();
       {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -595,13 +680,14 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
       __syncthreads();
       continue;
     }
+#endif
     FPH_DECL;
     for (;;) {
       // ---- Q x, M x, M^T lambda
-      cta_matvec(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
       if (s.m > 0) {
-        cta_matvec(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
-        cta_matvec(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
+        MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
+        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
       }
       __syncthreads();
       FPH(0);
@@ -667,6 +753,7 @@ int fused_smem_doubles(const View& v) {
   const int solve = nblk * SB64 + SB64 * SP65 + 4 * SB64;
   int m = ldlt > syrk ? ldlt : syrk;
   if (solve > m) m = solve;
+  if (MV_NBUF * MV_CHUNK > m) m = MV_NBUF * MV_CHUNK;
   return m;
 }
 
@@ -676,7 +763,7 @@ int fused_smem_doubles(const View& v) {
 // (no Bunch-Kaufman rows), and a panel that fits the shared memory of one CTA.
 bool fused_batch_applicable(const View& v) {
   if (v.full || v.s.hard_eq) return false;
-  if (v.N < 1) return false;
+  if (v.N < 1 || v.N > 512) return false;  // cta_matvec_tma keeps a lane's part of x in 8 double2 registers
   return (size_t)fused_smem_doubles(v) * sizeof(double) <= 200 * 1024;
 }
 
