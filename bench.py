@@ -52,6 +52,15 @@ def make_cfg3(n, m, seed):
     return dict(Q=Q, c=c, A=A, l_A=mid - 0.25, u_A=mid + 0.25, l_x=-np.ones(n), u_x=np.ones(n))
 
 
+def static_config(n, m, N, world):
+    """The `config` both arms print (identical keys and values: the driver compares them); run-dependent numbers
+    (residuals, wall time, the reference arm's sample) live in `details` / `cpu_baseline.sample`."""
+    return {"workload": "cfg3: dense QP n=%d m=%d, normal-equations reduction; step = out-of-place LDL^T "
+                        "(root-free Cholesky) of the condensed KKT + 2 triangular solves" % (n, m),
+            "N": N, "flops_per_step": flops_factor_solve(N), "parallelism": "replicas x%d" % world,
+            "l2": "input matrix %.0f MB > 126 MB L2, re-read from HBM every step" % (N * N * 8 / 1e6)}
+
+
 def condensed_block(d, ns):
     """Leading ns x ns block of K = Hx + A^T W A at the reference's initial point (all slacks
     and duals 1: Hx = Q + 2I, W = 2I) -- the CPU sample matrix of the reference arm."""
@@ -160,6 +169,7 @@ def reference_arm(args):
     """The reference's own CPU implementation of the path (oracle/_ref = unmodified sources),
     one single-threaded replica per host core, on a bounded sample of the cfg3 workload."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     import multiprocessing as mp
@@ -199,14 +209,16 @@ def reference_arm(args):
     wall = time.perf_counter() - t0
     tmax = max(o[0] for o in outs)
     value = cores * steps * flops_factor_solve(ns) / tmax * 1e-12
-    sample = ("ldlt_decomposition + 2x overwriting_solve_ldlt on the leading %dx%d block of the cfg3 "
-              "condensed KKT, one single-threaded replica per core" % (ns, ns))
+    sample = ("each step = LinearSolvers::ldlt_decomposition + 2x overwriting_solve_ldlt on the leading %dx%d block "
+              "of the cfg3 condensed KKT (the full N = 8192 step is ~90 s per core: bounded sample, same TFLOP/s "
+              "metric, flops counted for the sample size), one single-threaded replica per host core" % (ns, ns))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": tmax / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "cfg3 sample: n=%d leading block of the n=8192 m=4096 condensed KKT" % ns,
-                   "residual": max(o[1] for o in outs), "wall_s": wall},
+        "config": static_config(CFG3["n"], CFG3["m"], CFG3["n"], world) if not args.quick else
+        static_config(2 * ns, ns, 2 * ns, world),
+        "details": {"residual": max(o[1] for o in outs), "wall_s": wall, "sample_n": ns},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -286,8 +298,11 @@ def ours(args):
     syrk_tf = prof["syrk_flops"] / (prof["syrk_ms"] * 1e-3) * 1e-12 if prof["syrk_ms"] > 0 else 0.0
     step_ms = ms_dev / args.steps
     factor_only_ms = fac.run(args.steps, 0) / args.steps
-    peak_src = ("live DMMA issue-rate probe (ipmz_fp64_peak_probe); MEASURED_PEAKS.json has no FP64 entry; "
-                "cuBLAS DGEMM 8192^3 on this pool = 36.0 TFLOP/s (profiles/r01_fp64_ceilings.log)")
+    peak_src = {"used": "live DMMA issue-rate probe (ipmz_fp64_peak_probe), this run", "probe_tflops": peak,
+                "cublas_dgemm_8192_tflops": 36.0, "cusolver_dpotrf_8192_tflops": 23.8,
+                "library_numbers_from": "profiles/r01_fp64_ceilings.log (tools/fp64_probe.cu on this pool)",
+                "note": "MEASURED_PEAKS.json has no FP64 entry; against cuBLAS DGEMM the fractions are x%.3f" %
+                        (peak / 36.0 if peak else 0.0)}
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
@@ -391,6 +406,11 @@ def ours(args):
                   "(ipmz_probe_kernels); the three vector passes move < 1 MB and measure launch latency",
            "kernels": hbm_kernels}
 
+    # ---- the other BASELINE.json configs, end to end through the C ABI (rank 0, single GPU) ----
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = bench_configs(z, args, local)
+
     # ---- batched IPM solves/s (cfg4), sharded by problem index, no collective ----
     batched = None
     if not args.no_batched:
@@ -412,11 +432,12 @@ def ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3: dense QP n=%d m=%d, normal-equations reduction; step = out-of-place LDL^T "
-                                   "(root-free Cholesky) of the condensed KKT + 2 triangular solves" % (n, m),
-                       "N": N, "flops_per_step": flops_step, "parallelism": "replicas x%d" % world,
-                       "l2": "input matrix %.0f MB > 126 MB L2, re-read from HBM every step" % (N * N * 8 / 1e6),
-                       "solution_residual": resid, "wall_s": wall},
+            "config": static_config(n, m, N, world),
+            "details": {"solution_residual": resid, "wall_s": wall},
+            "scaling_note": "value at n_gpus > 1 is n_gpus independent replicas of the single-GPU factorization (a "
+                            "single large KKT does not shard: DESIGN section 5); the sharded workload is `batched` "
+                            "(cfg4, strong scaling)",
+            "configs": configs,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "hbm": hbm, "batched": batched,
         }
@@ -427,12 +448,96 @@ def ours(args):
     return 0
 
 
+def bench_configs(z, args, local):
+    """cfg1 (n=200, m_eq=100, box; normal-equations reduction), cfg2 (n=2048, m=1024; augmented quasi-definite LDL^T)
+    and cfg5 (n=4096 portfolio, eps=1e-6; augmented): whole solve from pinned host buffers through the C ABI
+    (ipmz_create: H2D; ipmz_solve; ipmz_get_iterate: D2H), best of 2 after one warm-up."""
+    import problems as P
+    cases = [("cfg1", "n=200 m_eq=100 eq(SlackedSlacks)+box, normal equations", lambda: P.eq_box(200, 100, 1), z.NORMAL),
+             ("cfg2", "n=2048 m=1024 ineq+box, augmented quasi-definite LDL^T", lambda: P.ineq_box(2048, 1024, 2, kind="shift"),
+              z.AUGMENTED),
+             ("cfg5", "n=4096 portfolio eps=1e-6 near convergence, augmented LDL^T", lambda: P.portfolio(4096, 32, 1e-6, 5),
+              z.AUGMENTED)]
+    if args.quick:
+        cases = cases[:1]
+    out = {}
+    for name, what, make, red in cases:
+        q = make()
+        pin = {}
+        for k in ("Q", "c", "A", "l_A", "u_A", "C", "d", "l_x", "u_x"):
+            v = getattr(q, k)
+            if v is not None:
+                pin[k] = z.pinned_empty(v.shape)
+                pin[k][...] = v
+        pr = z.Problem(pin["Q"], pin["c"], pin.get("A"), pin.get("l_A"), pin.get("u_A"), pin.get("C"), pin.get("d"),
+                       pin["l_x"], pin["u_x"], q.ineq_bounds, q.var_bounds, q.equalities)
+        best, r = None, None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            sv = z.Solver(pr, z.Options(reduction=red, device=local))
+            r = sv.solve()
+            it = sv.iterate()
+            sv.close()
+            dt = time.perf_counter() - t0
+            if rep > 0 and (best is None or dt < best):
+                best = dt
+        Nred = q.n if red == z.NORMAL else q.N
+        out[name] = {"workload": what, "reduction": "normal" if red == z.NORMAL else "augmented", "N": Nred,
+                     "e2e_ms": best * 1e3, "device_loop_ms": r.solve_ms, "iterations": r.iterations,
+                     "converged": bool(r.converged), "ms_per_iteration": r.solve_ms / max(1, r.iterations), "f": r.f,
+                     "h2d_bytes": sum(int(v.nbytes) for v in pin.values()), "d2h_bytes": int(it.nbytes),
+                     "factor_solve_tflops_device": r.iterations * flops_factor_solve(Nred) / (r.solve_ms * 1e-3) * 1e-12}
+    return out
+
+
+def _cpu_solve_worker(args_):
+    """One host process of the batched CPU baseline: the reference's own Optimizer::solve on cfg4 problems."""
+    seeds, kind = args_
+    import oracle_lib as ol
+    import problems as P
+    t0 = time.perf_counter()
+    its = []
+    for sd in seeds:
+        q = P.ineq_box(CFG4["n"], CFG4["m"], sd, kind="shift")
+        tr = ol.ref_solve(q, quiet=True, steps=False) if kind == "reference" else ol.port_solve(q, steps=False)
+        its.append((tr.iterations, float(tr.f[min(tr.iterations, tr.n_logged - 1)]) if kind != "reference" else None))
+    return time.perf_counter() - t0, its
+
+
+def batched_cpu_baseline(per_core=2):
+    """one reference process per host core over cfg4 problems (Optimizer ctor + solve(), stdout
+    disabled), core count stated.  Also the same-run parity gate's oracle values (port: it exposes f)."""
+    import multiprocessing as mp
+    import oracle_lib as ol
+    kind = "reference" if ol.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    seeds = [[CFG4["seed0"] + c * per_core + j for j in range(per_core)] for c in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        outs = pool.map(_cpu_solve_worker, [(sd, kind) for sd in seeds])
+        wall = time.perf_counter() - t0
+        gate = pool.map(_cpu_solve_worker, [([CFG4["seed0"] + i], "port") for i in range(16)])
+    nsolved = cores * per_core
+    return ({"value": nsolved / wall, "unit": "solves/s", "cores": cores, "kind": kind,
+             "sample": "%d cfg4 QPs (%d per core), one single-threaded %s process per host core, Optimizer ctor + solve() "
+                       "with stdout disabled; wall %.2f s" % (nsolved, per_core, kind, wall),
+             "per_core_solves_per_s": nsolved / wall / cores},
+            [g[1][0] for g in gate])
+
+
 def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
     import problems as P
+    import torch
     total = CFG4["count"] if not args.quick else 64
     n, m = CFG4["n"], CFG4["m"]
     lo, hi = z.shard_range(total, world, rank)
     cnt = hi - lo
+    if cnt <= 0:  # more ranks than problems: this rank only takes part in the barriers / reductions
+        for _ in range(9):
+            barrier()
+        allmax(0.0); allmax(0.0); allmax(0.0); allsum(0.0); allsum(0.0); allmax(0.0)
+        return None
     keys = ("Q", "c", "A", "l_A", "u_A", "l_x", "u_x")
     shapes = dict(Q=(cnt, n, n), c=(cnt, n), A=(cnt, m, n), l_A=(cnt, m), u_A=(cnt, m), l_x=(cnt, n), u_x=(cnt, n))
     pin = {k: z.pinned_empty(shapes[k]) for k in keys}
@@ -441,54 +546,89 @@ def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
         for k in keys:
             pin[k][i] = getattr(q, k)
     red = z.NORMAL if args.batch_reduction == "normal" else z.AUGMENTED
-    # this rank's share as `groups` concurrent sub-batches (one host thread + stream each inside the library):
-    # the latency-bound kernels of one sub-batch overlap the throughput-bound kernels of another
-    groups = max(1, min(args.batch_groups, cnt // 64))
-    cuts = [g * cnt // groups for g in range(groups + 1)]
-    subs = []
-    for g in range(groups):
-        lo_g, hi_g = cuts[g], cuts[g + 1]
-        sp = z.Problem(*(pin[k][lo_g:hi_g] for k in ("Q", "c", "A", "l_A", "u_A")), None, None,
-                       pin["l_x"][lo_g:hi_g], pin["u_x"][lo_g:hi_g])
-        subs.append(z.BatchSolver(sp, hi_g - lo_g, z.Options(reduction=red, device=local)))
+    # one handle per rank: the whole share runs in ONE persistent kernel (one CTA per problem at a time, problems
+    # pulled from a ticket counter).  End to end the kernel is launched first and consumes problems as the copy
+    # stream delivers them in `chunks` groups (ipmz_batch_solve_streamed): upload and solve overlap.
+    sp = z.Problem(*(pin[k] for k in ("Q", "c", "A", "l_A", "u_A")), None, None, pin["l_x"], pin["u_x"])
+    bs = z.BatchSolver(sp, cnt, z.Options(reduction=red, device=local))
+    chunks = max(1, min(args.batch_chunks, cnt // 16))
     xout = z.pinned_empty((cnt, n))
     h2d = sum(int(v.nbytes) for v in pin.values())
-    dev_ms, e2e_s, iters, conv = [], [], None, 0
-    import torch
+    dev_ms, e2e_s, up_s, iters, conv = [], [], [], None, 0
+    launches0 = z.launch_count()
     for rep in range(3):
-        # end to end: H2D of the problem data (asynchronous, per sub-batch stream: the upload of one
-        # sub-batch overlaps the solve of another) + solve + D2H of x
+        # end to end: H2D of the problem data + solve + D2H of x, all ranks at once
         barrier()
         t0 = time.perf_counter()
-        for b_ in subs:
-            b_.upload()
-        z.solve_group(subs)
-        for g, b_ in enumerate(subs):
-            b_.x(xout[cuts[g]:cuts[g + 1]])
+        bs.solve_streamed(chunks=chunks, per_problem=False)
+        bs.x(xout)
         e2e_s.append(time.perf_counter() - t0)
-        # device-resident: data already in HBM when the timed region starts
-        for b_ in subs:
-            b_.upload()
-        torch.cuda.synchronize()
+        # the upload alone, all ranks at once: the H2D floor of the end-to-end number
         barrier()
-        dev_ms.append(z.solve_group(subs))
+        t0 = time.perf_counter()
+        bs.upload()
+        torch.cuda.synchronize()
+        up_s.append(time.perf_counter() - t0)
+        # device-resident: data already in HBM when the timed region starts
+        barrier()
+        dev_ms.append(bs.solve(per_problem=False)[1])
         if rep == 2:
-            res = [r for b_ in subs for r in b_.results()]
+            res = bs.results()
             iters = [r.iterations for r in res]
             conv = sum(1 for r in res if r.converged)
-    for b_ in subs:
-        b_.close()
+            xs = xout.copy()
+            fs = [r.f for r in res[:16]]
+    launches = z.launch_count() - launches0
+    bs.close()
     t_dev = allmax(min(dev_ms[1:])) * 1e-3
     t_e2e = allmax(min(e2e_s[1:]))
+    t_up = allmax(min(up_s[1:]))
     nconv = allsum(conv)
-    return {"metric": "ipm_solves_per_sec", "workload": "cfg4: %d independent QPs n=%d m=%d (ineq + box), sharded by "
-            "problem index over %d GPU(s), no collective; %d concurrent sub-batches per GPU" % (total, n, m, world, groups),
-            "reduction": args.batch_reduction,
-            "value": total / t_dev, "unit": "solves/s", "scaling": "strong",
-            "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": int(xout.nbytes), "seconds": t_e2e},
-            "device_seconds": t_dev, "converged": int(nconv), "iterations_mean": float(np.mean(iters)),
-            "iterations_max": int(np.max(iters))}
+    it_sum = allsum(float(np.sum(iters)))
+    it_max = int(allmax(float(np.max(iters))))
+    floor = max(t_dev, t_up)
+    out = {"metric": "ipm_solves_per_sec", "workload": "cfg4: %d independent QPs n=%d m=%d (ineq + box), sharded by "
+           "problem index over %d GPU(s), no collective; one persistent kernel per GPU (k_ipm_batch: one CTA per "
+           "problem, whole Mehrotra loop on the device, no host round trip)" % (total, n, m, world),
+           "reduction": args.batch_reduction,
+           "value": total / t_dev, "unit": "solves/s", "scaling": "strong",
+           "e2e": {"value": total / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": int(xout.nbytes), "seconds": t_e2e, "upload_chunks": chunks,
+                   "call": "ipmz_batch_solve_streamed (kernel launched first, problems consumed as the copy stream "
+                           "delivers them) + ipmz_batch_get_x",
+                   "upload_only_seconds": t_up, "h2d_gbs_per_rank": h2d / t_up * 1e-9,
+                   "h2d_gbs_aggregate": world * h2d / t_up * 1e-9,
+                   "floor_seconds": floor, "floor": "max(device time, concurrent upload time of all ranks)",
+                   "e2e_over_floor": t_e2e / floor},
+           "device_seconds": t_dev, "converged": int(nconv), "iterations_mean": it_sum / total,
+           "iterations_max": it_max,
+           "gpu_launches": launches,
+           "gpu_launches_note": "3 repetitions x (streamed solve: 1 kernel; upload: transpose + initial point; "
+                                "device-resident solve: 1 kernel)",
+           "algorithmic": {"flops_per_problem_iteration": n * n * m + n ** 3 / 3.0,
+                           "note": "condensed assembly n^2 m + LDL^T n^3/3 (FP64 DMMA); input bytes per problem %d"
+                                   % ((n * n + m * n + 3 * n + 2 * m) * 8)}}
+    out["tflops_device"] = it_sum * out["algorithmic"]["flops_per_problem_iteration"] / t_dev * 1e-12
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu, gate_its = batched_cpu_baseline()
+            out["cpu_baseline"] = cpu
+            import oracle_lib as ol
+            dfs = []
+            for i in range(16):
+                q = P.ineq_box(n, m, CFG4["seed0"] + i, kind="shift")
+                tr = ol.port_solve(q, steps=False)
+                dfs.append(abs(fs[i] - tr.f[tr.iterations]) / max(1.0, abs(tr.f[tr.iterations])))
+                gate_its[i] = tr.iterations
+            out["parity_gate"] = {"problems": 16, "oracle": "port (bit-for-bit the reference on every golden case)",
+                                  "iterations_equal": [int(v) for v in iters[:16]] == [int(v) for v in gate_its],
+                                  "max_rel_df": float(max(dfs)), "tolerance": 1e-8,
+                                  "pass": bool([int(v) for v in iters[:16]] == [int(v) for v in gate_its] and
+                                               max(dfs) <= 1e-8)}
+        except Exception as e:  # reported, never substituted
+            out["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": 0, "kind": "reference",
+                                   "sample": "failed: %r" % (e,)}
+    return out
 
 
 def main():
@@ -497,12 +637,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sample-n", type=int, default=2048, help="CPU sample size of the reference arm")
+    ap.add_argument("--sample-n", type=int, default=3072, help="CPU sample size of the reference arm")
     ap.add_argument("--cores", type=int, default=0)
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batch-reduction", default="normal", choices=["normal", "augmented"])
-    ap.add_argument("--batch-groups", type=int, default=4, help="concurrent sub-batches (handles/streams) per GPU")
+    ap.add_argument("--batch-chunks", type=int, default=16, help="upload groups of the streamed end-to-end batch solve")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg2 / cfg5 end-to-end solves")
     ap.add_argument("--quick", action="store_true", help="small sizes (debug only; not a valid bench line)")
     args = ap.parse_args()
     if args.impl == "reference":

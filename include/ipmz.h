@@ -213,11 +213,18 @@ int ipmz_factor_get_ld(ipmz_factor_handle h, double* L_host, double* D_host);
 int ipmz_batch_create(int count, const ipmz_problem* shape_and_data, const ipmz_options* opt,
                       ipmz_batch_handle* out);
 int ipmz_batch_destroy(ipmz_batch_handle h);
-/* Upload (again) the problem data from host arrays laid out as at create; part of the
- * end-to-end timed region of bench.py. */
+/* Upload (again) the problem data from host arrays laid out as at create (same shape and Settings: checked); part of
+ * the end-to-end timed region of bench.py.  The copies are asynchronous: page-locked host arrays must stay untouched
+ * until the next ipmz_batch_solve* / ipmz_batch_get_* call on the handle has returned. */
 int ipmz_batch_upload(ipmz_batch_handle h, const ipmz_problem* data);
+/* Every solve restarts the per-problem counters and continues from the handle's current iterates (after an upload: the
+ * reference's initial point; after a solve: warm start, 0 iterations when already converged). */
 int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem /* count entries or NULL */,
                      double* ms_total);
+/* Upload + solve pipelined: the persistent batch kernel starts first and takes problems as the copy stream delivers the
+ * `chunks` groups of host data (laid out as for ipmz_batch_upload); one launch, upload and solve overlap. */
+int ipmz_batch_solve_streamed(ipmz_batch_handle h, const ipmz_problem* data, int chunks,
+                              ipmz_result* per_problem /* count entries or NULL */, double* ms_total);
 /* g batches of ONE device solved concurrently, one host thread + CUDA stream per handle (latency-bound
  * kernels of one sub-batch overlap throughput-bound kernels of another); ms_total = device time from the
  * earliest start to the latest end. Per-problem results: ipmz_batch_get_x / _get_iterates per handle. */

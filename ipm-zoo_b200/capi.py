@@ -116,6 +116,7 @@ def lib():
         L.ipmz_batch_destroy.argtypes = [vp]
         L.ipmz_batch_upload.argtypes = [vp, C.POINTER(_Problem)]
         L.ipmz_batch_solve.argtypes = [vp, C.POINTER(_Result), dp]
+        L.ipmz_batch_solve_streamed.argtypes = [vp, C.POINTER(_Problem), C.c_int, C.POINTER(_Result), dp]
         L.ipmz_batch_get_iterates.argtypes = [vp, dp]
         L.ipmz_batch_get_x.argtypes = [vp, dp]
         L.ipmz_batch_solve_group.argtypes = [C.c_int, C.POINTER(vp), dp]
@@ -328,6 +329,15 @@ class BatchSolver:
         arr = (_Result * self.count)() if per_problem else None
         ms = C.c_double()
         _check(lib().ipmz_batch_solve(self._h, arr, C.byref(ms)))
+        return ([Result(r) for r in arr] if per_problem else None), ms.value
+
+    def solve_streamed(self, problem=None, chunks=8, per_problem=True):
+        """Upload + solve pipelined (ipmz_batch_solve_streamed): the persistent kernel takes problems as the copy stream
+        delivers the `chunks` groups of host data."""
+        ps = (problem or self.p).c_struct()
+        arr = (_Result * self.count)() if per_problem else None
+        ms = C.c_double()
+        _check(lib().ipmz_batch_solve_streamed(self._h, C.byref(ps), chunks, arr, C.byref(ms)))
         return ([Result(r) for r in arr] if per_problem else None), ms.value
 
     def results(self):

@@ -69,6 +69,14 @@ struct FusedArgs {
   int* ticket;
   int refine_fixed;  // >= 0: that many refinement steps per condensed solve; -1: by the problem's mu (solver.cu policy)
   int smem_doubles;
+  // streamed solve (ipmz_batch_solve_streamed): the kernel is launched BEFORE the problem data is uploaded; `ready` is a
+  // device word the copy stream overwrites (4-byte H2D copy, stream-ordered after each chunk of problems) with the number
+  // of problems whose data is resident.  A CTA holding ticket p waits until *ready > p, then builds the reference's
+  // initial point and the transposed copy M^T itself (the upload path's k_initial_point / k_transpose could not be
+  // scheduled while this persistent grid owns every SM).  nullptr: everything is resident already.
+  const volatile int* ready;
+  int* abort_flag;   // set when a wait on `ready` times out (the host returns an error instead of hanging the GPU)
+  double* MT_w;      // writable alias of v.MT for the in-kernel transpose
   int dbg;  // experiments (IPMZ_FUSED_DBG): 1 = only the opening matvecs (30x), 2 = assembly (20x), 3 = + LDL^T, 4 = + one solve
 };
 
@@ -649,6 +657,45 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
     __syncthreads();
     if (p >= a.count) break;
     Scal& sc = v.sc[p];
+    if (a.ready) {
+      __shared__ int s_ok;
+      if (tid == 0) {
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*a.ready <= p) {
+          __nanosleep(2000);
+          if (clock64() - t0 > (8ll << 30)) { ok = 0; break; }  // ~4 s: the upload never arrived
+        }
+        if (!ok) atomicExch(a.abort_flag, 1);
+        s_ok = ok;
+        __threadfence();
+      }
+      __syncthreads();
+      if (!s_ok) {
+        if (tid == 0) { sc.iters = 0; sc.done = 3; }
+        __syncthreads();
+        continue;
+      }
+      // initial point (EnvironmentBuilder.cpp:34-73) and M^T, as ipmz_batch_upload's kernels would have left them
+      for (int i = tid; i < len; i += FT) initial_point_body(v, p, i);
+      if (s.m > 0) {
+        const double* M = v.M + (size_t)p * v.sM;
+        double* MT = a.MT_w + (size_t)p * v.sMT;
+        const int lane = tid & 31, warp = tid >> 5;
+        double* tile = sm + warp * (32 * 33);
+        const int tr = (s.m + 31) >> 5, tc = (s.n + 31) >> 5;
+        for (int t = warp; t < tr * tc; t += FW) {
+          const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+          for (int i = 0; i < 32; ++i)
+            tile[i * 33 + lane] = (r0 + i < s.m && c0 + lane < s.n) ? M[(size_t)(r0 + i) * v.ldm + c0 + lane] : 0.0;
+          __syncwarp();
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < s.n && r0 + lane < s.m) MT[(size_t)(c0 + i) * v.ldmt + r0 + lane] = tile[lane * 33 + i];
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+    }
     if (tid == 0) {  // a fresh solve restarts the counters and keeps the iterate (warm start, as ipmz_solve)
       sc.iters = 0; sc.done = 0; sc.mu_c = 0.0; sc.alpha = 0.0; sc.alpha_aff = 0.0; sc.sigma = 0.0;
     }
@@ -754,6 +801,7 @@ int fused_smem_doubles(const View& v) {
   int m = ldlt > syrk ? ldlt : syrk;
   if (solve > m) m = solve;
   if (MV_NBUF * MV_CHUNK > m) m = MV_NBUF * MV_CHUNK;
+  if (FW * 32 * 33 > m) m = FW * 32 * 33;  // one 32 x 33 transpose tile per warp (streamed mode)
   return m;
 }
 
@@ -781,8 +829,12 @@ int fused_batch_init() {
 
 // One launch: every problem of the batch from its current iterate to convergence.  `ticket` is a device int the
 // launcher resets on the stream.  Returns a cudaError_t.
-int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket) {
+int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket, const int* ready,
+                     int* abort_flag) {
   FusedArgs a;
+  a.ready = ready;
+  a.abort_flag = abort_flag;
+  a.MT_w = const_cast<double*>(v.MT);
   a.v = v;
   a.v.active = nullptr;
   a.count = count;

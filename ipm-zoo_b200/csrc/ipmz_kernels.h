@@ -139,7 +139,9 @@ void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const doubl
 bool fused_batch_applicable(const View& v);  // AUGMENTED / NORMAL, LDL^T rows only, panel fits one CTA's shared memory
 int fused_batch_init();                      // per-device opt-in shared-memory size; returns cudaError_t
 // every problem 0..count-1 from its current iterate to convergence; refine_fixed < 0 = refinement by each problem's mu
-int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket);
+// ready != nullptr: streamed mode -- the grid is launched before the upload and a CTA waits until *ready > its ticket
+int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket,
+                     const int* ready = nullptr, int* abort_flag = nullptr);
 int fused_read_clocks(unsigned long long* out16);  // debug builds (-DIPMZ_FUSED_CLOCKS)
 
 // ---- trsv.cu ----

@@ -113,6 +113,12 @@ struct Workspace {
   int Naug = 0;
   bool fused = false;         // batch handles: the persistent one-CTA-per-problem kernel (batch_fused.cu)
   int* fused_ticket = nullptr;
+  // streamed solve: copy stream, the device word it overwrites with the number of resident problems, abort flag
+  cudaStream_t cps = nullptr;
+  cudaEvent_t ev_arm = nullptr;
+  int* ready_dev = nullptr;
+  int* abort_dev = nullptr;
+  int* ready_host = nullptr;  // pinned: cumulative problem counts per chunk (the source of the 4-byte copies)
   int refine = 0;  // iterative-refinement steps of the normal reduction
   int refine_extra = 0;   // +1 on the late iterations of a single QP (run_ipm), see there
   bool refine_auto = false;
@@ -137,6 +143,9 @@ struct Workspace {
     for (void* p : allocs) cudaFree(p);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_arm) cudaEventDestroy(ev_arm);
+    if (ready_host) cudaFreeHost(ready_host);
+    if (cps) cudaStreamDestroy(cps);
     if (st) cudaStreamDestroy(st);
   }
   template <class T>
@@ -188,47 +197,62 @@ static int upload_pitched(double* dst, int ld, const double* src, int cols, size
   return IPMZ_OK;
 }
 
-static int upload_data(Workspace& w, const ipmz_problem* p) {
+// the reference's bound checks (EnvironmentBuilder.cpp:10-17) over problems [q0, q1)
+static int check_bounds(const Workspace& w, const ipmz_problem* p, int q0, int q1) {
   const Shape& s = w.v.s;
-  const int count = w.count;
-  const int me = s.m - s.mi;
-  int rc;
-  // the reference's bound checks (EnvironmentBuilder.cpp:10-17)
-  for (size_t i = 0; i < (size_t)count * s.n; ++i)
+  for (size_t i = (size_t)q0 * s.n; i < (size_t)q1 * s.n; ++i)
     if (!(p->l_x[i] < p->u_x[i])) return fail(IPMZ_ERR_BOUNDS, "l_x < u_x violated");
-  for (size_t i = 0; i < (size_t)count * s.mi; ++i)
+  for (size_t i = (size_t)q0 * s.mi; i < (size_t)q1 * s.mi; ++i)
     if (!(p->l_A[i] <= p->u_A[i])) return fail(IPMZ_ERR_BOUNDS, "l_A <= u_A violated");
-  if ((rc = upload_pitched(w.Q, w.v.ldq, p->Q, s.n, (size_t)count * s.n, w.st))) return rc;
-  if ((rc = upload_pitched(w.c, s.ns, p->c, s.n, count, w.st))) return rc;
-  if ((rc = upload_pitched(w.lx, s.ns, p->l_x, s.n, count, w.st))) return rc;
-  if ((rc = upload_pitched(w.ux, s.ns, p->u_x, s.n, count, w.st))) return rc;
+  return IPMZ_OK;
+}
+
+// H2D of the data of problems [q0, q1) on stream `st` (host arrays hold all `count` problems back to back)
+static int upload_range(Workspace& w, const ipmz_problem* p, int q0, int q1, cudaStream_t st) {
+  const Shape& s = w.v.s;
+  const int me = s.m - s.mi;
+  const size_t C = (size_t)(q1 - q0), o = (size_t)q0;
+  if (q1 <= q0) return IPMZ_OK;
+  int rc;
+  if ((rc = upload_pitched(w.Q + o * w.v.sQ, w.v.ldq, p->Q + o * s.n * s.n, s.n, C * s.n, st))) return rc;
+  if ((rc = upload_pitched(w.c + o * s.ns, s.ns, p->c + o * s.n, s.n, C, st))) return rc;
+  if ((rc = upload_pitched(w.lx + o * s.ns, s.ns, p->l_x + o * s.n, s.n, C, st))) return rc;
+  if ((rc = upload_pitched(w.ux + o * s.ns, s.ns, p->u_x + o * s.n, s.n, C, st))) return rc;
   if (s.m > 0) {
     if (s.mi > 0 && me == 0) {
-      if ((rc = upload_pitched(w.M, w.v.ldm, p->A, s.n, (size_t)count * s.mi, w.st))) return rc;
-      if ((rc = upload_pitched(w.lo, s.ms, p->l_A, s.mi, count, w.st))) return rc;
-      if ((rc = upload_pitched(w.up, s.ms, p->u_A, s.mi, count, w.st))) return rc;
+      if ((rc = upload_pitched(w.M + o * w.v.sM, w.v.ldm, p->A + o * s.mi * s.n, s.n, C * s.mi, st))) return rc;
+      if ((rc = upload_pitched(w.lo + o * s.ms, s.ms, p->l_A + o * s.mi, s.mi, C, st))) return rc;
+      if ((rc = upload_pitched(w.up + o * s.ms, s.ms, p->u_A + o * s.mi, s.mi, C, st))) return rc;
     } else if (s.mi == 0) {
-      if ((rc = upload_pitched(w.M, w.v.ldm, p->C, s.n, (size_t)count * me, w.st))) return rc;
-      if ((rc = upload_pitched(w.lo, s.ms, p->d, me, count, w.st))) return rc;
-      if ((rc = upload_pitched(w.up, s.ms, p->d, me, count, w.st))) return rc;
+      if ((rc = upload_pitched(w.M + o * w.v.sM, w.v.ldm, p->C + o * me * s.n, s.n, C * me, st))) return rc;
+      if ((rc = upload_pitched(w.lo + o * s.ms, s.ms, p->d + o * me, me, C, st))) return rc;
+      if ((rc = upload_pitched(w.up + o * s.ms, s.ms, p->d + o * me, me, C, st))) return rc;
     } else {
-      for (int q = 0; q < count; ++q) {
+      for (int q = q0; q < q1; ++q) {
         double* Mq = w.M + (size_t)q * w.v.sM;
-        if ((rc = upload_pitched(Mq, w.v.ldm, p->A + (size_t)q * s.mi * s.n, s.n, s.mi, w.st))) return rc;
-        if ((rc = upload_pitched(Mq + (size_t)s.mi * w.v.ldm, w.v.ldm, p->C + (size_t)q * me * s.n, s.n, me, w.st)))
+        if ((rc = upload_pitched(Mq, w.v.ldm, p->A + (size_t)q * s.mi * s.n, s.n, s.mi, st))) return rc;
+        if ((rc = upload_pitched(Mq + (size_t)s.mi * w.v.ldm, w.v.ldm, p->C + (size_t)q * me * s.n, s.n, me, st)))
           return rc;
         CUDA_TRY(cudaMemcpyAsync(w.lo + (size_t)q * s.ms, p->l_A + (size_t)q * s.mi, sizeof(double) * s.mi,
-                                 cudaMemcpyHostToDevice, w.st));
+                                 cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(w.up + (size_t)q * s.ms, p->u_A + (size_t)q * s.mi, sizeof(double) * s.mi,
-                                 cudaMemcpyHostToDevice, w.st));
+                                 cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(w.lo + (size_t)q * s.ms + s.mi, p->d + (size_t)q * me, sizeof(double) * me,
-                                 cudaMemcpyHostToDevice, w.st));
+                                 cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(w.up + (size_t)q * s.ms + s.mi, p->d + (size_t)q * me, sizeof(double) * me,
-                                 cudaMemcpyHostToDevice, w.st));
+                                 cudaMemcpyHostToDevice, st));
       }
     }
-    launch_transpose(w.st, count, w.M, w.v.ldm, w.v.sM, w.MT, w.v.ldmt, w.v.sMT, s.m, s.n);
   }
+  return IPMZ_OK;
+}
+
+static int upload_data(Workspace& w, const ipmz_problem* p) {
+  const Shape& s = w.v.s;
+  int rc;
+  if ((rc = check_bounds(w, p, 0, w.count))) return rc;
+  if ((rc = upload_range(w, p, 0, w.count, w.st))) return rc;
+  if (s.m > 0) launch_transpose(w.st, w.count, w.M, w.v.ldm, w.v.sM, w.MT, w.v.ldmt, w.v.sMT, s.m, s.n);
   CUDA_TRY(cudaGetLastError());
   return IPMZ_OK;
 }
@@ -315,6 +339,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
   ALLOC(w->fused_ticket, 1);
+  ALLOC(w->ready_dev, 1); ALLOC(w->abort_dev, 1);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
 #undef ALLOC
   v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
@@ -490,6 +515,11 @@ static int run_ipm(Workspace& w, double* ms_out) {
   for (int i = 0; i < count; ++i) w.active_host[i] = i;
   bool identity = true;
   CUDA_TRY(cudaEventRecord(w.ev0, w.st));
+  if (count > 1 || w.fused) {
+    // batch handles: a solve restarts the per-problem counters and keeps the iterates (warm start, as ipmz_solve);
+    // without this a second solve would see done != 0 everywhere and return the previous results at once
+    CUDA_TRY(cudaMemsetAsync(v.sc, 0, sizeof(Scal) * count, w.st));
+  }
   if (w.fused) {
     // one launch: every problem runs its whole predictor-corrector loop inside a persistent CTA; the host reads the
     // per-problem records once, at the end
@@ -920,10 +950,26 @@ int ipmz_batch_destroy(ipmz_batch_handle h) {
   return IPMZ_OK;
 }
 
+// the caller's problem arrays must have the handle's shape and Settings
+static int check_same_shape(const ipmz_batch_s* h, const ipmz_problem* data) {
+  int rc = check_problem(data);
+  if (rc) return rc;
+  Shape s;
+  fill_shape(s, data);
+  const Shape& t = h->w->v.s;
+  if (data->m_ineq != h->mi_host || data->m_eq != h->me_host || s.n != t.n || s.m != t.m || s.mi != t.mi ||
+      s.ylo != t.ylo || s.zup != t.zup || s.ilo != t.ilo || s.iup != t.iup || s.hard_eq != t.hard_eq || s.reg_eq != t.reg_eq)
+    return fail(IPMZ_ERR_ARG, "problem data does not match the shape / Settings the batch handle was created with");
+  return IPMZ_OK;
+}
+
+// The copies are asynchronous (stream-ordered before the next solve): with page-locked host arrays the caller must
+// leave them untouched until the next ipmz_batch_solve* / ipmz_batch_get_* on this handle has returned.
 int ipmz_batch_upload(ipmz_batch_handle h, const ipmz_problem* data) {
   if (!h || !data) return fail(IPMZ_ERR_ARG, "null argument");
   Workspace& w = *h->w;
   int rc;
+  if ((rc = check_same_shape(h, data))) return rc;
   if ((rc = ensure_device(w.device))) return rc;
   if ((rc = upload_data(w, data))) return rc;
   View v = w.v;
@@ -942,6 +988,71 @@ int ipmz_batch_solve(ipmz_batch_handle h, ipmz_result* per_problem, double* ms_t
   if (ms_total) *ms_total = ms;
   if (per_problem)
     for (int q = 0; q < w.count; ++q) fill_result(w, q, per_problem + q, ms);
+  return IPMZ_OK;
+}
+
+// Upload + solve as ONE pipelined operation (the end-to-end path of bench.py): the persistent batch kernel is launched
+// first and its CTAs pick up problems as the copy stream delivers them -- the data of `chunks` groups of problems is
+// uploaded group by group, each followed by a 4-byte copy that publishes the number of resident problems; the kernel
+// builds the initial point and M^T itself.  Upload and solve overlap down to the first chunk; one launch, no host
+// round trip.  Host arrays as for ipmz_batch_upload (all problems back to back); ms_total = device time from the
+// launch to the last result.  Only handles on the persistent-kernel path (otherwise: upload, then solve).
+int ipmz_batch_solve_streamed(ipmz_batch_handle h, const ipmz_problem* data, int chunks, ipmz_result* per_problem,
+                              double* ms_total) {
+  if (!h || !data) return fail(IPMZ_ERR_ARG, "null argument");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = check_same_shape(h, data))) return rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  if (!w.fused) {
+    if ((rc = ipmz_batch_upload(h, data))) return rc;
+    return ipmz_batch_solve(h, per_problem, ms_total);
+  }
+  const int count = w.count;
+  if (chunks < 1) chunks = 1;
+  if (chunks > count) chunks = count;
+  if (chunks > 256) chunks = 256;
+  if ((rc = check_bounds(w, data, 0, count))) return rc;
+  if (!w.cps) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&w.cps, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&w.ev_arm, cudaEventDisableTiming));
+    CUDA_TRY(cudaHostAlloc((void**)&w.ready_host, sizeof(int) * 256, cudaHostAllocDefault));
+  }
+  View v = w.v;
+  v.active = nullptr;
+  CUDA_TRY(cudaMemsetAsync(w.ready_dev, 0, sizeof(int), w.st));
+  CUDA_TRY(cudaMemsetAsync(w.abort_dev, 0, sizeof(int), w.st));
+  CUDA_TRY(cudaEventRecord(w.ev_arm, w.st));
+  CUDA_TRY(cudaEventRecord(w.ev0, w.st));
+  const int e = launch_ipm_batch(w.st, v, count, w.refine_auto ? -1 : w.refine, w.fused_ticket, w.ready_dev, w.abort_dev);
+  if (e != 0) return fail(IPMZ_ERR_CUDA, std::string("launch_ipm_batch: ") + cudaGetErrorString((cudaError_t)e));
+  CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal) * count, cudaMemcpyDeviceToHost, w.st));
+  CUDA_TRY(cudaEventRecord(w.ev1, w.st));
+  // the copy stream starts once the ready word has been cleared
+  CUDA_TRY(cudaStreamWaitEvent(w.cps, w.ev_arm, 0));
+  int up_rc = IPMZ_OK;
+  for (int c = 0; c < chunks; ++c) {
+    const int q0 = (int)((long long)c * count / chunks), q1 = (int)((long long)(c + 1) * count / chunks);
+    if (up_rc == IPMZ_OK) up_rc = upload_range(w, data, q0, q1, w.cps);
+    // even after a failed copy the kernel must be released (it would otherwise wait for its time-out)
+    w.ready_host[c] = q1;
+    if (cudaMemcpyAsync(w.ready_dev, w.ready_host + c, sizeof(int), cudaMemcpyHostToDevice, w.cps) != cudaSuccess &&
+        up_rc == IPMZ_OK)
+      up_rc = fail(IPMZ_ERR_CUDA, "publishing the resident-problem count failed");
+  }
+  CUDA_TRY(cudaEventSynchronize(w.ev1));
+  CUDA_TRY(cudaStreamSynchronize(w.cps));
+  CUDA_TRY(cudaGetLastError());
+  if (up_rc) return up_rc;
+  int aborted = 0;
+  CUDA_TRY(cudaMemcpy(&aborted, w.abort_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (aborted) return fail(IPMZ_ERR_CUDA, "streamed batch solve: the kernel timed out waiting for problem data");
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+  h->last_ms = ms;
+  if (ms_total) *ms_total = ms;
+  if (per_problem)
+    for (int q = 0; q < count; ++q) fill_result(w, q, per_problem + q, ms);
   return IPMZ_OK;
 }
 

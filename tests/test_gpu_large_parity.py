@@ -11,9 +11,10 @@ step -- so the dataflow LDL^T, the streaming solves, the TMA condensed assembly 
 against the oracle where they run, not against each other.
 
 Tolerances (north_star): Newton step 1e-9 relative (norm-wise, max|d - d_ref| / max|d_ref|), same iteration count,
-final objective within 1e-8.  The one documented exception: cfg5's last iterations, where cond(K) ~ 1/mu ~ 1e8-1e9
-bounds the agreement of ANY two FP64 factorizations at cond * eps ~ 1e-7 ("hard parts"); there the
-bound is CFG5_LATE_TOL and the measured errors are written to gpurun_out/parity_large.json.
+final objective within 1e-8 -- everywhere, cfg5's last iterations (mu ~ 1e-8, cond(K) ~ 1/mu) included: measured
+8.3e-10 at worst (cfg5 eps = 1e-10, NORMAL reduction with its refinement steps, last iteration), 1e-15 .. 1e-10
+elsewhere; the kernels are bitwise reproducible, so the margin does not move between runs.  The measured errors are
+written to gpurun_out/parity_large.json (a copy of one run: profiles/r02_parity_large.json).
 """
 import json
 import os
@@ -28,7 +29,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 STEP_TOL = 1e-9
-CFG5_LATE_TOL = 1e-6
+CFG5_LATE_TOL = 1e-9
 MEASURED = {}
 
 
@@ -77,7 +78,7 @@ def check_traces(tr, g, k, key):
     em = float(np.max(np.abs(mu - g["mu"]) / np.maximum(np.abs(g["mu"]), 1e-12)))
     record(key, f=ef, res_rel=er, mu_rel=em)
     assert ef < 1e-8
-    assert er < 1e-3 and em < 1e-3
+    assert er < 1e-6 and em < 1e-8  # measured: res 4e-8 (NORMAL) / 2e-10, mu 2e-11
 
 
 @pytest.mark.parametrize("red", ["AUGMENTED", "NORMAL", "FULL"])

@@ -267,3 +267,57 @@ def test_batch_solve_group_matches_single_batch():
     assert [r.iterations for r in got] == [r.iterations for r in res]
     assert all(r.converged for r in got)
     assert np.array_equal(x_grp, x_one)
+
+
+def test_reset_iterate_after_set_iterate_is_the_fresh_initial_pack(z):
+    """ipmz_reset_iterate after ipmz_set_iterate reproduces the fresh initial pack bit for bit -- including the slots
+    of EqualityHandling::Regularization rows that no kernel reads (they used to keep what set_iterate wrote)."""
+    for p, eq in ((CASES["ineq_box_20x10"](), None), (CASES["eq_box_40x20"](), 3)):
+        zp = z.Problem.from_data(p)
+        if eq is not None:
+            zp.equalities = eq  # IPMZ_EQ_REGULARIZATION
+        s = z.Solver(zp)
+        fresh = s.iterate()
+        s.set_iterate(np.full(zp.iterate_len, 7.25))
+        assert not np.array_equal(s.iterate(), fresh)
+        s.reset_iterate()
+        assert np.array_equal(s.iterate(), fresh)
+        s.close()
+
+
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_batch_streamed_solve_matches_upload_then_solve(z, reduction):
+    """ipmz_batch_solve_streamed (kernel launched first, problems consumed as the copy stream delivers them, initial
+    point and M^T built inside the kernel) gives bitwise the results of ipmz_batch_upload + ipmz_batch_solve; a second
+    solve without a new upload is a warm start (0 iterations), not a stale copy of the first."""
+    count, n, m = 40, 48, 20
+    probs = [P.ineq_box(n, m, 900 + i, kind="shift") for i in range(count)]
+    st = lambda key: np.stack([getattr(q, key) for q in probs])
+    bp = z.Problem(st("Q"), st("c"), st("A"), st("l_A"), st("u_A"), None, None, st("l_x"), st("u_x"))
+    bs = z.BatchSolver(bp, count, z.Options(reduction=reduction))
+    res, ms = bs.solve()
+    x_ref = bs.x()
+    assert all(r.converged for r in res) and ms > 0
+    again, _ = bs.solve()
+    assert all(r.converged and r.iterations == 0 for r in again)
+    for chunks in (1, 7):
+        got, _ = bs.solve_streamed(chunks=chunks)
+        assert [r.iterations for r in got] == [r.iterations for r in res]
+        assert [r.f for r in got] == [r.f for r in res]
+        assert np.array_equal(bs.x(), x_ref)
+    bs.close()
+
+
+def test_batch_upload_rejects_a_different_shape(z):
+    count, n, m = 4, 24, 8
+    probs = [P.ineq_box(n, m, 50 + i) for i in range(count)]
+    st = lambda key: np.stack([getattr(q, key) for q in probs])
+    bp = z.Problem(st("Q"), st("c"), st("A"), st("l_A"), st("u_A"), None, None, st("l_x"), st("u_x"))
+    bs = z.BatchSolver(bp, count)
+    other = [P.ineq_box(n + 4, m, 60 + i) for i in range(count)]
+    so = lambda key: np.stack([getattr(q, key) for q in other])
+    bad = z.Problem(so("Q"), so("c"), so("A"), so("l_A"), so("u_A"), None, None, so("l_x"), so("u_x"))
+    with pytest.raises(z.IpmzError) as e:
+        bs.upload(bad)
+    assert e.value.code == 1
+    bs.close()
