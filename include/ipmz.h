@@ -153,6 +153,12 @@ int ipmz_solve(ipmz_handle h, ipmz_result* res);
  * corrector, as the reference prints them at Optimizer.cpp:359; any pointer may be NULL. */
 int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* alpha_aff,
                      double* sigma, double* alpha);
+/* What the reference leaves in the Environment besides the iterate (Optimizer.cpp:147-157, :188-209, :369, :377): the
+ * LAST Newton iteration's corrector direction (`\Delta v` keys), affine direction (`\Delta v_affine` keys), shorthand
+ * residuals r_* (corrector values: complementarity rows include the affine second-order term) -- each in the packed
+ * iterate layout, the entry of variable v at v's slot -- and the centred barrier parameter sigma*mu.  Any pointer may
+ * be NULL.  Meaningful after an ipmz_solve that took at least one iteration. */
+int ipmz_get_last_iteration(ipmz_handle h, double* delta, double* delta_affine, double* residuals, double* mu_centered);
 /* Per-iteration log of the last ipmz_solve: f/res/mu have iterations+1 entries (cap = how
  * many the caller's arrays hold); steps need record_steps and hold cap x (n+m) doubles. */
 int ipmz_get_trace(ipmz_handle h, int cap, double* f, double* res, double* mu, double* step_aff,

@@ -12,7 +12,9 @@
 //   3. flatten the Environment's ValMatrix / ValVector entries (Evaluation.h:12-22) into the
 //      contiguous row-major buffers of ipmz_problem and the packed iterate;
 //   4. ipmz_create + ipmz_set_iterate + ipmz_solve; write the final iterate back into env under
-//      the variable keys (Optimizer.cpp:228) so callers read results where they always did.
+//      the variable keys (Optimizer.cpp:228) so callers read results where they always did, and the
+//      rest of what the reference's solve() leaves there: the last iteration's `\Delta v` and
+//      `\Delta v_affine` directions, the shorthand residuals r_{v} and mu (ipmz_get_last_iteration).
 #include "ipmz_reference_adapter.h"
 
 #include <algorithm>
@@ -22,6 +24,7 @@
 
 #include "../include/ipmz.h"
 #include "Utils/Assert.h"
+#include "ExprFactory.h"
 #include "Utils/Helpers.h"
 
 namespace NumericalOptimization {
@@ -148,12 +151,48 @@ void B200Optimizer::solve() {
   iterations_ = r.iterations;
   converged_ = r.converged != 0;
   ipmz_check(ipmz_get_iterate(handle_, packed.data()));
+  auto slice = [&](const std::vector<double>& pk, size_t o, int len) {
+    return Evaluation::val_vector(std::vector<double>(pk.begin() + o, pk.begin() + o + len));
+  };
   off = 0;
   for (const auto& s : slots) {
-    if (s.len > 0 && has_var(newton_system_, s.key))
-      env_.at(s.key) = Evaluation::val_vector(std::vector<double>(packed.begin() + off, packed.begin() + off + s.len));
+    if (s.len > 0 && has_var(newton_system_, s.key)) env_.at(s.key) = slice(packed, off, s.len);
     off += s.len;
   }
+  if (iterations_ == 0) return;  // converged at the first test: the reference leaves the rest of env untouched too
+
+  // The rest of the reference's Environment contract: the last iteration's directions under the `\Delta v` keys
+  // (Optimizer.cpp:369, :377), the affine directions of the complementarity variables under `\Delta v_affine`
+  // (:104-112, :200), the shorthand residuals r_{v} with their corrector values (:188-209) and mu = sigma mu (:179).
+  std::vector<double> delta(total), daff(total), resid(total);
+  double mu_c = 0.0;
+  ipmz_check(ipmz_get_last_iteration(handle_, delta.data(), daff.data(), resid.data(), &mu_c));
+  using EF = Expression::ExprFactory;
+  const auto shorthand = SymbolicOptimization::get_shorthand_rhs(newton_system_);
+  // variables whose affine direction the reference stores: those of a shorthand definition that contains a vector of
+  // ones and mu (the complementarity rows), Optimizer.cpp:191-203
+  std::vector<ExprPtr> affine_vars;
+  for (const auto& [vec, expr] : shorthand.vector_definitions) {
+    if ((expr->contains_subexpression(oe_.e_var) || expr->contains_subexpression(oe_.e_ineq) ||
+         expr->contains_subexpression(oe_.e_eq)) &&
+        expr->contains_subexpression(oe_.mu))
+      for (const auto& var : expr->get_variables())
+        if (std::find(affine_vars.begin(), affine_vars.end(), var) == affine_vars.end()) affine_vars.push_back(var);
+  }
+  off = 0;
+  for (const auto& s : slots) {
+    if (s.len > 0 && has_var(newton_system_, s.key)) {
+      const auto dv = SymbolicOptimization::get_delta_variable(s.key);
+      env_[dv] = slice(delta, off, s.len);
+      if (std::find(affine_vars.begin(), affine_vars.end(), s.key) != affine_vars.end()) {
+        const auto& var = std::get<Expression::Variable>(dv->get_impl());
+        env_[EF::variable(var.name + "_affine")] = slice(daff, off, s.len);
+      }
+      env_[EF::named_vector("r_{" + s.key->to_string() + "}")] = slice(resid, off, s.len);
+    }
+    off += s.len;
+  }
+  env_.at(oe_.mu) = Evaluation::val_scalar(mu_c);
 }
 
 }  // namespace NumericalOptimization

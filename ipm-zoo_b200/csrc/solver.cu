@@ -132,6 +132,7 @@ struct Workspace {
   // trace of the last solve (single-problem handles)
   std::vector<double> tr_f, tr_res, tr_mu, tr_alpha_aff, tr_sigma, tr_alpha;
   double* steps_dev = nullptr;  // [max_iter][2][Naug] when record_steps
+  double* Rlast = nullptr;      // single QP: the shorthand residuals r_* of the last Newton iteration (corrector values)
   int tr_iters = 0;
   bool iterate_set = false;
 
@@ -340,6 +341,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
   ALLOC(w->fused_ticket, 1);
   ALLOC(w->ready_dev, 1); ALLOC(w->abort_dev, 1);
+  if (count == 1) ALLOC(w->Rlast, v.sp);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
 #undef ALLOC
   v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
@@ -501,6 +503,10 @@ static void newton_iteration(Workspace& w, const View& v, int nslots, bool updat
                         cudaMemcpyDeviceToDevice, w.st);
     }
   }
+  // the next iteration's (or the final stopping test's) residual pass overwrites R: keep the corrector's r_* for
+  // ipmz_get_last_iteration (the reference leaves them in the Environment, Optimizer.cpp:188-209)
+  if (w.Rlast && nslots == 1 && !v.active)
+    cudaMemcpyAsync(w.Rlast, v.R, sizeof(double) * v.sp, cudaMemcpyDeviceToDevice, w.st);
   if (update) launch_update(w.st, v, nslots);
 }
 
@@ -683,7 +689,11 @@ int ipmz_full_layout(const ipmz_problem* p, int* offsets12) {
 }
 
 // Copy between the caller's packed iterate(s) and the device packs. dir 0: host->device.
+static int move_pack(Workspace& w, int mi_host, int me_host, double* packed, int dir, double* devpack);
 static int move_iterates(Workspace& w, int mi_host, int me_host, double* packed, int dir) {
+  return move_pack(w, mi_host, me_host, packed, dir, w.v.V);
+}
+static int move_pack(Workspace& w, int mi_host, int me_host, double* packed, int dir, double* devpack) {
   const Shape& s = w.v.s;
   const int n = s.n, me_dev = s.m - s.mi;
   const HostLayout h = host_layout(n, mi_host, me_host);
@@ -691,7 +701,7 @@ static int move_iterates(Workspace& w, int mi_host, int me_host, double* packed,
   std::vector<double> dev(C * w.v.sp, 0.0);
   if (ensure_device(w.device)) return IPMZ_ERR_CUDA;
   // start from the current device contents so untouched padding / absent groups survive
-  CUDA_TRY(cudaMemcpy(dev.data(), w.v.V, sizeof(double) * dev.size(), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(dev.data(), devpack, sizeof(double) * dev.size(), cudaMemcpyDeviceToHost));
   for (size_t q = 0; q < C; ++q) {
     double* hp = packed + q * h.len;
     double* dp = dev.data() + q * w.v.sp;
@@ -712,7 +722,7 @@ static int move_iterates(Workspace& w, int mi_host, int me_host, double* packed,
       if (me_dev > 0) mv(hp + h.off_eq + (size_t)k * me_host, dm + (size_t)k * s.ms + s.mi, me_dev);
     }
   }
-  if (dir == 0) CUDA_TRY(cudaMemcpy(w.v.V, dev.data(), sizeof(double) * dev.size(), cudaMemcpyHostToDevice));
+  if (dir == 0) CUDA_TRY(cudaMemcpy(devpack, dev.data(), sizeof(double) * dev.size(), cudaMemcpyHostToDevice));
   return IPMZ_OK;
 }
 
@@ -810,6 +820,23 @@ int ipmz_newton_step(ipmz_handle h, double* step_aff, double* step_cor, double* 
   if (alpha_aff) *alpha_aff = w.sc_host[0].alpha_aff;
   if (sigma) *sigma = w.sc_host[0].sigma;
   if (alpha) *alpha = w.sc_host[0].alpha;
+  return IPMZ_OK;
+}
+
+int ipmz_get_last_iteration(ipmz_handle h, double* delta, double* delta_affine, double* residuals, double* mu_centered) {
+  if (!h) return fail(IPMZ_ERR_ARG, "null handle");
+  Workspace& w = *h->w;
+  int rc;
+  if ((rc = ensure_device(w.device))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(w.st));
+  if (delta && (rc = move_pack(w, h->mi_host, h->me_host, delta, 1, w.v.D))) return rc;
+  if (delta_affine && (rc = move_pack(w, h->mi_host, h->me_host, delta_affine, 1, w.v.DA))) return rc;
+  if (residuals && (rc = move_pack(w, h->mi_host, h->me_host, residuals, 1, w.Rlast))) return rc;
+  if (mu_centered) {
+    Scal sc;
+    CUDA_TRY(cudaMemcpy(&sc, w.v.sc, sizeof(Scal), cudaMemcpyDeviceToHost));
+    *mu_centered = sc.mu_c;
+  }
   return IPMZ_OK;
 }
 

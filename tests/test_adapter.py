@@ -167,3 +167,29 @@ def test_cli_demo_files_and_batch(tmp_path):
     open(bad, "w").write("n 2 bogus 1\n")
     out = run(bad)
     assert out.returncode == 1 and "unknown keyword" in out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SO), reason="adapter test library not prebuilt")
+@pytest.mark.parametrize("name", ["toy", "ineq_box_20x10", "eq_box_40x20", "box_30", "ineq_upper_box_lower_30x12"])
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_reference_adapter_environment_contract(name, reduction):
+    """Everything the UNMODIFIED reference Optimizer leaves in its Environment -- the iterate, the last iteration's
+    `\\Delta v` and `\\Delta v_affine` directions (Optimizer.cpp:369, :377, :200), the shorthand residuals r_{v}
+    (:147-157, :188-209) and mu (:179) -- is present in the adapter's Environment with the same values: the harness
+    runs both on identically built Environments and compares every key of the reference's."""
+    L = C.CDLL(SO)
+    p = CASES[name]()
+    out = np.zeros(4)
+    key = C.create_string_buffer(256)
+    err = C.create_string_buffer(512)
+    P = lambda a: a.ctypes.data_as(dp) if a is not None and a.size else None
+    rc = L.adapter_env_contract(p.n, p.m_ineq, p.m_eq, P(p.Q), P(p.c), P(p.A), P(p.l_A), P(p.u_A), P(p.C), P(p.d),
+                                P(p.l_x), P(p.u_x), p.ineq_bounds, p.var_bounds, int(p.equalities), reduction,
+                                P(out), key, 256, err, 512)
+    assert rc == 0, err.value.decode()
+    nkeys, missing, worst = int(out[0]), int(out[1]), out[2]
+    assert nkeys > 20
+    assert missing == 0, key.value.decode()
+    # directions of the last iteration are O(1e-9) themselves; entries are compared relative to max(1, |ref|_inf)
+    assert worst < 1e-7, "%s differs by %.3e" % (key.value.decode(), worst)
