@@ -74,9 +74,14 @@ enum {
 enum {
   IPMZ_REDUCTION_AUGMENTED = 0, /* quasi-definite [[Hx, M^T],[M, -W^-1]], LDL^T, N = n+m   */
   IPMZ_REDUCTION_NORMAL = 1,    /* primal condensed Hx + M^T W M, root-free Cholesky, N = n */
-  IPMZ_REDUCTION_FULL = 2       /* un-reduced Newton system (SymbolicOptimization.cpp:417-433), symmetrised and
+  IPMZ_REDUCTION_FULL = 2,      /* un-reduced Newton system (SymbolicOptimization.cpp:417-433), symmetrised and
                                    ordered so that unpivoted LDL^T performs the reference's block elimination;
                                    N = n + 2m + 2n*(sides of the box) + 2m*(sides of the rows) <= 5n + 6m */
+  IPMZ_REDUCTION_DUAL_NORMAL = 3 /* the reference's own "normal equations" (get_normal_equations,
+                                   SymbolicOptimization.cpp:465-478: row 0 = dx eliminated): root-free Cholesky of Hx
+                                   (n x n), S = W^-1 + M Hx^-1 M^T (m x m) formed by the panel solves + DMMA updates of
+                                   the rows of M, root-free Cholesky of S,  S dlam = M Hx^-1 b0 - b1,
+                                   dx = Hx^-1 (b0 - M^T dlam).  ipmz_assemble returns S (N_out = m). */
 };
 
 typedef struct {

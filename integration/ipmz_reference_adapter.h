@@ -19,7 +19,7 @@ namespace NumericalOptimization {
 
 class B200Optimizer {
  public:
-  enum class Reduction { Augmented = 0, Normal = 1, Full = 2 };
+  enum class Reduction { Augmented = 0, Normal = 1, Full = 2, DualNormal = 3 };
 
   B200Optimizer(Evaluation::Environment& env,
                 const SymbolicOptimization::OptimizationExpressions& optimization_expressions,

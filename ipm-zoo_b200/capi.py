@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-AUGMENTED, NORMAL, FULL = 0, 1, 2
+AUGMENTED, NORMAL, FULL, DUAL_NORMAL = 0, 1, 2, 3
 NONE, LOWER, UPPER, BOTH = 0, 1, 2, 3
 EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE, EQ_REGULARIZATION = 0, 1, 2, 3  # ipmz_problem.equalities (EqualityHandling)
 dp = C.POINTER(C.c_double)
@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "ipmz_factor_info", "ipmz_schedule_check", "ipmz_assembly_schedule_check",
     "ipmz_batch_create", "ipmz_batch_destroy", "ipmz_batch_upload", "ipmz_batch_solve",
     "ipmz_batch_get_iterates", "ipmz_batch_get_x", "ipmz_batch_solve_group", "ipmz_batch_results",
+    "ipmz_batch_solve_streamed", "ipmz_get_last_iteration",
 ]
 
 
@@ -296,7 +297,7 @@ class Solver:
         return [(self.PROBE_SLOTS[i], float(ms[i]), float(by[i])) for i in range(7)]
 
     def assemble(self):
-        N = self.p.N if self.opt.c.reduction != FULL else 5 * self.p.n + 6 * (self.p.N - self.p.n)
+        N = self.p.N if self.opt.c.reduction != FULL else 5 * self.p.n + 6 * (self.p.N - self.p.n)  # DUAL_NORMAL: m <= N
         K = np.zeros((N, N))
         nout = C.c_int()
         _check(lib().ipmz_assemble(self._h, _ptr(K), C.byref(nout)))

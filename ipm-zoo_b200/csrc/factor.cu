@@ -592,7 +592,8 @@ static double* wpanel_of(const FactorPlan& fp, int k0) {
 // diag + panel solve of the NB-wide block column at k0 (reads `in`, writes dst)
 static void launch_panel(cudaStream_t st, const FactorPlan& fp, const double* in, double* dst, double* Dg, int k0,
                          const LaunchHooks& hk) {
-  const int nb = fp.N - k0 < NB ? fp.N - k0 : NB;
+  const int ncols = fp.ncols > 0 ? fp.ncols : fp.N;
+  const int nb = ncols - k0 < NB ? ncols - k0 : NB;
   hk.begin(st, 0);
   k_diag_ldlt<<<dim3(1, fp.nslots), 256, DIAG_SMEM, st>>>(in, dst, fp.ld, fp.sK, Dg, fp.sD, fp.inv, fp.sInv, k0, nb,
                                                           fp.active);
@@ -643,6 +644,17 @@ static void launch_double_panel(cudaStream_t st, const FactorPlan& fp, const dou
 static void ldlt_schedule(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg,
                           const LaunchHooks& hk, bool allow_overlap) {
   const LookAhead* la = fp.la;
+  if (fp.ncols > 0 && fp.ncols < fp.N) {
+    // partial elimination (dual-Schur normal equations): the first ncols columns, one panel at a time; the last panel
+    // may be narrower than NB, the trailing update starts right after it
+    for (int k0 = 0; k0 < fp.ncols; k0 += NB) {
+      const int nb = fp.ncols - k0 < NB ? fp.ncols - k0 : NB;
+      const double* in = (k0 == 0) ? src : dst;
+      launch_panel(st, fp, in, dst, Dg, k0, hk);
+      launch_trailing(st, fp, in, dst, Dg, k0 + nb, k0, nb, 0, 0, hk);
+    }
+    return;
+  }
   const bool two_level = fp.N > 8 * NB;
   const bool overlap = allow_overlap && two_level && la && la->side;
   if (!two_level) {
@@ -676,8 +688,25 @@ static void ldlt_schedule(cudaStream_t st, const FactorPlan& fp, const double* s
   }
 }
 
+__global__ void k_negate_block(const double* __restrict__ src, int lds, size_t sS, double* __restrict__ dst, int ldd,
+                               size_t sD, int m, const int* __restrict__ active) {
+  const int p = active ? active[blockIdx.y] : blockIdx.y;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= m) return;
+  const double* s = src + (size_t)p * sS + (size_t)r * lds;
+  double* d = dst + (size_t)p * sD + (size_t)r * ldd;
+  for (int c = lane; c <= r; c += 32) d[c] = -s[c];
+}
+
+void launch_negate_block(cudaStream_t st, int nslots, const int* active, const double* src, int lds, size_t sS,
+                         double* dst, int ldd, size_t sD, int m) {
+  if (m <= 0 || nslots <= 0) return;
+  k_negate_block<<<dim3((m + 7) / 8, nslots), 256, 0, st>>>(src, lds, sS, dst, ldd, sD, m, active);
+  count_launch();
+}
+
 void launch_ldlt(cudaStream_t st, const FactorPlan& fp, const double* src, double* dst, double* Dg) {
-  if (fp.df && fp.nslots == 1 && !fp.active) {
+  if (fp.df && fp.nslots == 1 && !fp.active && !(fp.ncols > 0 && fp.ncols < fp.N)) {
     launch_ldlt_dataflow(st, *fp.df, src, dst, Dg, fp.inv);
     return;
   }

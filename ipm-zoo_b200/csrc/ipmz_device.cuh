@@ -103,6 +103,7 @@ struct View {
   size_t sK;
   int ldk, N, normal;      // N = n+m (augmented), n (normal) or FullLayout::N (full)
   int full;                // 1: un-reduced system in the FullLayout order
+  int dual;                // 1: dual-Schur normal equations: K = augmented matrix, factorized in two stages (Hx, then S)
   FullLayout fl;
   Scal* sc;
   const int* active;       // slot -> problem index (nullptr: identity)

@@ -108,6 +108,8 @@ struct FactorPlan {
   size_t sInv = 0;
   double* wpanel = nullptr;  // [nslots][2][N x 256] W = L D of the current panels (pre-scaled B operand)
   size_t sW = 0;
+  int ncols = 0;  // > 0: eliminate only the first ncols columns (the rows below them are solved and every trailing
+                  // block is updated: afterwards the block [ncols, N)^2 holds the Schur complement); 0 = all N
   const LookAhead* la = nullptr;  // nullptr: single-stream schedule
   DataflowPlan* df = nullptr;     // set (single large matrix): launch_ldlt runs the persistent dataflow kernel
 };
@@ -143,6 +145,12 @@ int fused_batch_init();                      // per-device opt-in shared-memory 
 int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket,
                      const int* ready = nullptr, int* abort_flag = nullptr);
 int fused_read_clocks(unsigned long long* out16);  // debug builds (-DIPMZ_FUSED_CLOCKS)
+
+// dst[m x ldd](lower) = -src block (lower), the Schur complement left by a partial elimination, as its own matrix
+void launch_negate_block(cudaStream_t st, int nslots, const int* active, const double* src, int lds, size_t sS,
+                         double* dst, int ldd, size_t sD, int m);
+// dual-Schur normal equations, vector steps between the solves (see solver.cu dual_solve)
+void launch_dual_vec(cudaStream_t st, const View& v, int nslots, int stage, const double* rvec, double* lam);
 
 // ---- trsv.cu ----
 int trsv_init();  // opt-in shared memory size of the streaming solves

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -109,6 +110,9 @@ struct Workspace {
   TrsvWork tw{};
   LookAhead la{};
   DataflowPlan* df = nullptr;  // single large QP: persistent dataflow LDL^T
+  // dual-Schur normal equations: S = W^-1 + M Hx^-1 M^T as its own m x m matrix, its pivots and factorization scratch
+  double *S = nullptr, *Dg2 = nullptr, *inv2 = nullptr, *wpanel2 = nullptr;
+  int ldS = 0;
   AssemblyPlan* asmp = nullptr;  // single large QP, NORMAL: condensed assembly as UPD tasks of the dataflow kernel
   int Naug = 0;
   bool fused = false;         // batch handles: the persistent one-CTA-per-problem kernel (batch_fused.cu)
@@ -266,10 +270,20 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   ipmz_options opt;
   if (opt_in) opt = *opt_in; else ipmz_default_options(&opt);
   if (opt.reduction != IPMZ_REDUCTION_AUGMENTED && opt.reduction != IPMZ_REDUCTION_NORMAL &&
-      opt.reduction != IPMZ_REDUCTION_FULL)
+      opt.reduction != IPMZ_REDUCTION_FULL && opt.reduction != IPMZ_REDUCTION_DUAL_NORMAL)
     return fail(IPMZ_ERR_ARG, "unknown reduction");
   if ((rc = ensure_device(opt.device))) return rc;
 
+  const bool timing = getenv("IPMZ_CREATE_TIMING") != nullptr;  // debug: host wall time of the phases of create
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto t_start = tnow();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    const auto t = tnow();
+    fprintf(stderr, "[ipmz_create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_start).count());
+    t_start = t;
+  };
   Workspace* w = new Workspace();
   std::unique_ptr<Workspace> guard(w);
   w->device = opt.device;
@@ -285,11 +299,15 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.s.delta_eq = opt.delta_eq > 0.0 ? opt.delta_eq : 1e-4;
   if (s.reg_eq && opt.reduction == IPMZ_REDUCTION_FULL)
     return fail(IPMZ_ERR_ARG, "EqualityHandling::Regularization is available in the AUGMENTED and NORMAL reductions");
+  if (opt.reduction == IPMZ_REDUCTION_DUAL_NORMAL && (s.m == 0 || s.reg_eq))
+    return fail(IPMZ_ERR_ARG, "the dual-Schur normal equations need constraint rows with slacks (no rows: Hx alone is "
+                              "the AUGMENTED reduction; EqualityHandling::Regularization: AUGMENTED or NORMAL)");
   if (s.hard_eq && opt.reduction != IPMZ_REDUCTION_AUGMENTED)
     return fail(IPMZ_ERR_ARG, "EqualityHandling::None (indefinite KKT, Bunch-Kaufman) is available in the AUGMENTED reduction only");
   w->Naug = s.n + s.m;
   v.normal = (opt.reduction == IPMZ_REDUCTION_NORMAL) ? 1 : 0;
   v.full = (opt.reduction == IPMZ_REDUCTION_FULL) ? 1 : 0;
+  v.dual = (opt.reduction == IPMZ_REDUCTION_DUAL_NORMAL) ? 1 : 0;
   v.fl = full_layout(s);
   v.N = v.normal ? s.n : (v.full ? v.fl.N : w->Naug);
   v.ldk = pad4(v.N);
@@ -309,7 +327,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (count == 1) {
     const int le = lookahead_create(&w->la);
     if (le != 0) return fail(IPMZ_ERR_CUDA, std::string("lookahead_create: ") + cudaGetErrorString((cudaError_t)le));
-    if (dataflow_min_n() > 0 && v.N >= dataflow_min_n()) {
+    if (dataflow_min_n() > 0 && v.N >= dataflow_min_n() && !v.dual) {
       const int de = dataflow_plan_create(&w->df, v.N, v.ldk);
       if (de != 0) return fail(IPMZ_ERR_CUDA, std::string("dataflow_plan_create: ") + cudaGetErrorString((cudaError_t)de));
       if (v.normal && s.m > 0) {
@@ -320,6 +338,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   }
   CUDA_TRY(cudaEventCreate(&w->ev0));
   CUDA_TRY(cudaEventCreate(&w->ev1));
+  lap("streams + plans");
   const size_t C = (size_t)count;
 #define ALLOC(ptr, n) if ((rc = w->alloc(&(ptr), (n)))) return rc
   ALLOC(w->Q, C * v.sQ); ALLOC(w->M, C * v.sM); ALLOC(w->MT, C * v.sMT);
@@ -333,6 +352,11 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   ALLOC(v.K, C * v.sK); ALLOC(v.Dg, C * v.ldk); ALLOC(w->inv, C * factor_inv_stride(v.ldk));
   ALLOC(w->wpanel, C * factor_wpanel_stride(v.N));
   if (v.normal) ALLOC(w->MTW, C * v.sMT);
+  if (v.dual) {
+    w->ldS = pad4(s.m);
+    ALLOC(w->S, C * (size_t)s.m * w->ldS); ALLOC(w->Dg2, C * w->ldS);
+    ALLOC(w->inv2, C * factor_inv_stride(w->ldS)); ALLOC(w->wpanel2, C * factor_wpanel_stride(s.m));
+  }
   ALLOC(v.sc, C); ALLOC(v.partials, C * v.maxblk * 8); ALLOC(v.counters, C);
   ALLOC(w->active_dev, C);
   ALLOC(w->refine_dev, C);
@@ -348,15 +372,18 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.active = nullptr;
   {
     const char* e = getenv("IPMZ_BATCH_FUSED");
-    w->fused = batch_handle && fused_batch_applicable(v) && !(e && atoi(e) == 0);
+    w->fused = batch_handle && !v.dual && fused_batch_applicable(v) && !(e && atoi(e) == 0);
   }
+  lap("device allocations + memset");
   if (!w->sc_host.resize(count)) return fail(IPMZ_ERR_ALLOC, "cudaHostAlloc of the Scal mirror failed");
   w->active_host.resize(count);
 
+  lap("pinned Scal mirror");
   if ((rc = upload_data(*w, p))) return rc;
   launch_initial_point(w->st, v, count);
   CUDA_TRY(cudaStreamSynchronize(w->st));
   CUDA_TRY(cudaGetLastError());
+  lap("H2D + transpose + initial point");
   guard.release();
   *out = w;
   return IPMZ_OK;
@@ -370,6 +397,53 @@ static FactorPlan plan_of(const Workspace& w, int nslots, const int* active) {
   fp.la = (w.count == 1 && w.la.side) ? &w.la : nullptr;
   fp.df = (w.count == 1 && nslots == 1 && !active) ? w.df : nullptr;
   return fp;
+}
+
+// dual-Schur normal equations: the three factor plans over the augmented matrix K
+static FactorPlan dual_plan_stage1(const Workspace& w, int nslots, const int* active) {  // eliminate the n columns of Hx
+  FactorPlan fp = plan_of(w, nslots, active);
+  fp.df = nullptr; fp.la = nullptr;
+  fp.ncols = w.v.s.n;
+  return fp;
+}
+static FactorPlan dual_plan_hx(const Workspace& w, int nslots, const int* active) {  // solves with the factor of Hx
+  FactorPlan fp = plan_of(w, nslots, active);
+  fp.df = nullptr; fp.la = nullptr;
+  fp.N = w.v.s.n;
+  return fp;
+}
+static FactorPlan dual_plan_s(const Workspace& w, int nslots, const int* active) {  // S: m x m, its own buffers
+  FactorPlan fp;
+  fp.N = w.v.s.m; fp.ld = w.ldS; fp.sK = (size_t)w.v.s.m * w.ldS; fp.sD = (size_t)w.ldS; fp.nslots = nslots;
+  fp.active = active;
+  fp.inv = w.inv2; fp.sInv = factor_inv_stride(w.ldS);
+  fp.wpanel = w.wpanel2; fp.sW = factor_wpanel_stride(w.v.s.m);
+  return fp;
+}
+
+// K (augmented, assembled) -> factor of Hx in its leading block, S = -(Schur complement) as its own matrix, factor of S
+static void dual_factor(Workspace& w, const View& v, int nslots, bool factor_s = true) {
+  const Shape& s = v.s;
+  const FactorPlan f1 = dual_plan_stage1(w, nslots, v.active);
+  launch_ldlt(w.st, f1, v.K, v.K, v.Dg);
+  launch_negate_block(w.st, nslots, v.active, v.K + (size_t)s.n * v.ldk + s.n, v.ldk, v.sK, w.S, w.ldS,
+                      (size_t)s.m * w.ldS, s.m);
+  if (factor_s) launch_ldlt(w.st, dual_plan_s(w, nslots, v.active), w.S, w.S, w.Dg2);
+}
+
+// one Newton solve of the dual-Schur normal equations; the result lands in v.sol as [dx; dlam]
+static void dual_solve(Workspace& w, const View& v, int nslots) {
+  const Shape& s = v.s;
+  const FactorPlan fh = dual_plan_hx(w, nslots, v.active), fs = dual_plan_s(w, nslots, v.active);
+  launch_dual_vec(w.st, v, nslots, 0, v.rhs, v.tm);
+  launch_ldlt_solve(w.st, fh, v.K, v.Dg, v.sol, v.ssol, w.tw);
+  launch_matvec(w.st, nslots, v.active, v.M, v.ldm, v.sM, s.m, s.n, v.sol, v.ssol, v.Mx, s.ms);
+  launch_dual_vec(w.st, v, nslots, 1, v.rhs, v.tm);
+  launch_ldlt_solve(w.st, fs, w.S, w.Dg2, v.tm, s.ms, w.tw);
+  launch_matvec(w.st, nslots, v.active, v.MT, v.ldmt, v.sMT, s.n, s.m, v.tm, s.ms, v.tn, s.ns);
+  launch_dual_vec(w.st, v, nslots, 2, v.rhs, v.tm);
+  launch_ldlt_solve(w.st, fh, v.K, v.Dg, v.sol, v.ssol, w.tw);
+  launch_dual_vec(w.st, v, nslots, 3, v.rhs, v.tm);
 }
 
 // matvecs that open an iteration: Q x, M x, M^T lambda
@@ -428,7 +502,9 @@ static void newton_direction(Workspace& w, const View& v, int nslots, int mode) 
     launch_full_unpack(w.st, v, nslots, mode);
     return;
   }
-  if (!v.normal) {
+  if (v.dual) {
+    dual_solve(w, v, nslots);
+  } else if (!v.normal) {
     const FactorPlan fp = plan_of(w, nslots, v.active);
     launch_prepare_sol(w.st, v, nslots, v.rhs, 0);
     if (s.hard_eq) {
@@ -487,6 +563,8 @@ static void newton_iteration(Workspace& w, const View& v, int nslots, bool updat
   if (v.s.hard_eq) {
     const int e = launch_bk_factor(w.st, nslots, v.active, v.K, v.ldk, v.sK, v.N, w.ipiv, (size_t)v.ldk, 0);
     if (e != 0 && w.launch_error == 0) w.launch_error = e;
+  } else if (v.dual) {
+    dual_factor(w, v, nslots);
   } else launch_ldlt(w.st, fp, v.K, v.K, v.Dg);
   newton_direction(w, v, nslots, 0);
   launch_mu_affine(w.st, v, nslots);
@@ -882,6 +960,17 @@ int ipmz_assemble(ipmz_handle h, double* K_host, int* N_out) {
   iteration_matvecs(w, v, 1);
   launch_residuals_rhs(w.st, v, 1, 0);
   assemble_and_factor(w, v, 1);
+  if (v.dual) {  // S = W^-1 + M Hx^-1 M^T (the matrix of the reference's normal equations, sign flipped to SPD)
+    dual_factor(w, v, 1, false);
+    CUDA_TRY(cudaStreamSynchronize(w.st));
+    const int m = v.s.m;
+    CUDA_TRY(cudaMemcpy2D(K_host, sizeof(double) * m, w.S, sizeof(double) * w.ldS, sizeof(double) * m, m,
+                          cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; ++i)
+      for (int j = i + 1; j < m; ++j) K_host[(size_t)i * m + j] = K_host[(size_t)j * m + i];
+    if (N_out) *N_out = m;
+    return IPMZ_OK;
+  }
   CUDA_TRY(cudaStreamSynchronize(w.st));
   const int N = v.N;
   CUDA_TRY(cudaMemcpy2D(K_host, sizeof(double) * N, v.K, sizeof(double) * v.ldk, sizeof(double) * N, N,

@@ -221,6 +221,30 @@ __global__ void k_aug_residual(View v) {
   aug_residual_body(v, problem_of(v), blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// Dual-Schur normal equations (the reference's get_normal_equations, SymbolicOptimization.cpp:465-478): the vector
+// steps between the three triangular solves of one Newton solve, rvec = augmented right-hand side b0|b1:
+//   0: sol = b0                      -> Hx y = b0
+//   1: lam = M y - b1                -> S dlam = M Hx^-1 b0 - b1
+//   2: sol = b0 - M^T dlam           -> Hx dx = b0 - M^T dlam
+//   3: sol[n ..] = dlam              (augmented layout [dx; dlam] for the back-substitution)
+__global__ void k_dual_vec(View v, int stage, const double* __restrict__ rvec_all, double* __restrict__ lam_all) {
+  const int p = problem_of(v);
+  const Shape& s = v.s;
+  const double* rvec = rvec_all + (size_t)p * (s.ns + s.ms);
+  double* sol = v.sol + (size_t)p * v.ssol;
+  double* lam = lam_all + (size_t)p * s.ms;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stage == 0) {
+    if (i < s.n) sol[i] = rvec[i];
+  } else if (stage == 1) {
+    if (i < s.m) lam[i] = v.Mx[(size_t)p * s.ms + i] - rvec[s.ns + i];
+  } else if (stage == 2) {
+    if (i < s.n) sol[i] = rvec[i] - v.tn[(size_t)p * s.ns + i];
+  } else {
+    if (i < s.m) sol[s.n + i] = lam[i];
+  }
+}
+
 // Back-substitution + step length (bodies: vector_bodies.cuh).  MODE 0 writes the affine direction DA and
 // alpha_aff, MODE 1 the final direction D and alpha.
 template <int MODE>
@@ -325,6 +349,9 @@ void launch_recover_dual(cudaStream_t st, const View& v, int nslots, const doubl
 }
 void launch_aug_residual(cudaStream_t st, const View& v, int nslots) {
   k_aug_residual<<<vec_grid(v, nslots), TPB, 0, st>>>(v); count_launch();
+}
+void launch_dual_vec(cudaStream_t st, const View& v, int nslots, int stage, const double* rvec, double* lam) {
+  k_dual_vec<<<vec_grid(v, nslots), TPB, 0, st>>>(v, stage, rvec, lam); count_launch();
 }
 void launch_backsub_step(cudaStream_t st, const View& v, int nslots, int mode) {
   if (mode == 0) k_backsub_step<0><<<vec_grid(v, nslots), TPB, 0, st>>>(v);

@@ -212,7 +212,7 @@ int main(int argc, char** argv) {
       else if (a == "--reduction") {
         const std::string r = next();
         reduction = r == "augmented" ? IPMZ_REDUCTION_AUGMENTED : r == "normal" ? IPMZ_REDUCTION_NORMAL
-                  : r == "full" ? IPMZ_REDUCTION_FULL : -1;
+                  : r == "full" ? IPMZ_REDUCTION_FULL : r == "dual" ? IPMZ_REDUCTION_DUAL_NORMAL : -1;
         if (reduction < 0) throw AssertionError("unknown reduction '" + r + "'");
       } else if (a == "--equalities") {
         const std::string r = next();

@@ -57,7 +57,8 @@ struct Data {
 // name -> value, the numeric part of Evaluation::Environment (Evaluation.h:22)
 using Environment = std::map<std::string, Vector>;
 
-enum class Reduction { Augmented = IPMZ_REDUCTION_AUGMENTED, Normal = IPMZ_REDUCTION_NORMAL, Full = IPMZ_REDUCTION_FULL };
+enum class Reduction { Augmented = IPMZ_REDUCTION_AUGMENTED, Normal = IPMZ_REDUCTION_NORMAL, Full = IPMZ_REDUCTION_FULL,
+                       DualNormal = IPMZ_REDUCTION_DUAL_NORMAL };
 
 // Validates the bounds like the reference (EnvironmentBuilder.cpp:10-17) and returns the
 // reference's initial point keyed by variable name (EnvironmentBuilder.cpp:34-73).

@@ -81,7 +81,7 @@ def check_traces(tr, g, k, key):
     assert er < 1e-6 and em < 1e-8  # measured: res 4e-8 (NORMAL) / 2e-10, mu 2e-11
 
 
-@pytest.mark.parametrize("red", ["AUGMENTED", "NORMAL", "FULL"])
+@pytest.mark.parametrize("red", ["AUGMENTED", "NORMAL", "FULL", "DUAL_NORMAL"])
 def test_cfg2_reference_golden_steps_and_solve(z, red):
     g = np.load(os.path.join(GOLD, "cfg2_ineq_box_2048x1024.npz"))
     p = P.ineq_box(2048, 1024, 2, kind="shift")

@@ -147,7 +147,14 @@ def test_assemble_full_matches_model(z, name, k):
     assert np.array_equal(Kg, Kg.T)
 
 
+def _needs_rows(p, reduction):
+    """DUAL_NORMAL (3) eliminates dx onto the constraint rows: systems without rows have no such reduction."""
+    if reduction == 3 and p.m_ineq + p.m_eq == 0:
+        pytest.skip("no constraint rows: the dual-Schur normal equations do not exist")
+
+
 def _step_parity(z, p, iterate, reduction, tol=STEP_TOL):
+    _needs_rows(p, reduction)
     tr = ol.port_solve(p, cap_iters=1, stop_after_cap=True, iterate=iterate)
     s = z.Solver(z.Problem.from_data(p), z.Options(reduction=reduction))
     if iterate is not None:
@@ -162,13 +169,13 @@ def _step_parity(z, p, iterate, reduction, tol=STEP_TOL):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("reduction", [0, 1, 2])
+@pytest.mark.parametrize("reduction", [0, 1, 2, 3])
 def test_newton_step_at_initial_point(z, name, reduction):
     _step_parity(z, CASES[name](), None, reduction)
 
 
 @pytest.mark.parametrize("name", ["ineq_box_64x32", "eq_box_40x20", "cfg1_eq_box_200x100", "cfg4_unit_256x128"])
-@pytest.mark.parametrize("reduction", [0, 1, 2])
+@pytest.mark.parametrize("reduction", [0, 1, 2, 3])
 @pytest.mark.parametrize("k", [2, 4])
 def test_newton_step_at_reference_iterate(z, name, reduction, k):
     """Feed the CUDA path the oracle's iterate after k iterations, compare that iteration's steps."""
@@ -178,10 +185,11 @@ def test_newton_step_at_reference_iterate(z, name, reduction, k):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("reduction", [0, 1, 2])
+@pytest.mark.parametrize("reduction", [0, 1, 2, 3])
 def test_full_solve_matches_reference_golden(z, name, reduction):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     p = CASES[name]()
+    _needs_rows(p, reduction)
     s = z.Solver(z.Problem.from_data(p), z.Options(reduction=reduction, record_steps=True))
     r = s.solve()
     k = int(g["iterations"])
@@ -190,6 +198,10 @@ def test_full_solve_matches_reference_golden(z, name, reduction):
     assert abs(r.f - g["f"][k]) <= F_TOL * max(1.0, abs(g["f"][k]))
     tr = s.trace(k, steps=True)
     np.testing.assert_allclose(tr["f"][:k + 1], g["f"], rtol=1e-7, atol=1e-8)
+    # residual norm and mean complementarity of every iteration (Optimizer.cpp:129-130) against the reference's trace:
+    # the trajectories share every Newton step to ~1e-9, entries near the 1e-8 tolerance get an absolute allowance
+    np.testing.assert_allclose(tr["res"][:k + 1], g["res"], rtol=1e-5, atol=1e-11)
+    np.testing.assert_allclose(tr["mu"][:k + 1], g["mu"], rtol=1e-5, atol=1e-13)
     # first iteration's steps start from identical iterates
     assert relerr(tr["step_aff"][0], g["step_aff"][0]) < STEP_TOL
     assert relerr(tr["step_cor"][0], g["step_cor"][0]) < STEP_TOL
@@ -208,7 +220,7 @@ def test_warm_start_second_solve_is_immediate(z):
     s.close()
 
 
-@pytest.mark.parametrize("reduction", [0, 1, 2])
+@pytest.mark.parametrize("reduction", [0, 1, 2, 3])
 def test_batch_matches_oracle_per_problem(z, reduction):
     count, n, m = 12, 48, 20
     probs = [P.ineq_box(n, m, 2000 + i, kind="shift") for i in range(count)]
@@ -321,3 +333,23 @@ def test_batch_upload_rejects_a_different_shape(z):
         bs.upload(bad)
     assert e.value.code == 1
     bs.close()
+
+
+@pytest.mark.parametrize("name", ["ineq_box_64x32", "eq_box_40x20", "cfg4_unit_256x128", "ineq_only_30x12"])
+def test_dual_schur_matrix_matches_the_oracle_kkt(z, name):
+    """IPMZ_REDUCTION_DUAL_NORMAL: the matrix the CUDA path factorizes is the reference's normal-equations block
+    -(W^-1 + M Hx^-1 M^T) (SymbolicOptimization.cpp:465-478), sign flipped: checked against the Schur complement of the
+    oracle's assembled augmented KKT matrix at the oracle's iterate after two iterations."""
+    p = CASES[name]()
+    it = ol.port_solve(p, cap_iters=2, stop_after_cap=True).iterate.copy()
+    N, n = p.N, p.n
+    K = np.zeros((N, N))
+    ol.port().orc_assemble_kkt(p.c_struct(), ol._ptr(it), ol._ptr(K), None)
+    S_ref = -(K[n:, n:] - K[n:, :n] @ np.linalg.solve(K[:n, :n], K[:n, n:]))
+    s = z.Solver(z.Problem.from_data(p), z.Options(reduction=z.DUAL_NORMAL))
+    s.set_iterate(it)
+    S = s.assemble()
+    s.close()
+    assert S.shape == (N - n, N - n)
+    assert relerr(S, S_ref) < 1e-11
+    assert np.all(np.linalg.eigvalsh(S) > 0)
