@@ -59,9 +59,25 @@ constexpr int FT = 256;          // threads per CTA
 constexpr int FW = FT / 32;      // warps
 constexpr int PP = 36;           // panel pitch: 36 mod 16 == 4 -> conflict-free DMMA fragment loads
 constexpr int TS = 64;           // assembly tile
-constexpr int FSTAGES = 3;
-constexpr int STAGE_DOUBLES = 2 * TS * LDT;  // A-side + B-side rows of one 16-wide k-slice
-constexpr int SB64 = 64, SP65 = 65;  // block of the triangular sweeps
+#ifndef IPMZ_FSTAGES
+#define IPMZ_FSTAGES 3
+#endif
+constexpr int FSTAGES = IPMZ_FSTAGES;
+constexpr int PA = TS + 4;      // pitch of a k-slice row (68 mod 16 == 4: conflict-free DMMA fragment loads down a column)
+constexpr int STAGE_DOUBLES = 2 * BK * PA;  // A-side + B-side columns of one 16-row slice of M
+constexpr int SB64 = 64;  // block of the triangular sweeps
+// The reduced matrix / its factor live TILE-MAJOR in global memory in the fused path: the lower triangle as 64 x 64 tiles
+// (tile (tr, tc), tc <= tr, at index tr (tr + 1) / 2 + tc), each tile stored with the pitch it has in shared memory.  A
+// triangular sweep then fetches a tile with ONE bulk copy (35 KB contiguous; 64 row copies of 512 B each were bound by
+// the copy engine's per-instruction cost: 4500 cycles per tile), and the footprint of K shrinks from N ldk to about
+// 0.55 N^2 doubles.  Rows / columns past N and the pitch padding are never written and stay zero from the allocation.
+constexpr int TP = 70;               // tile pitch: rows 16-byte aligned; 70 * 8 B = 140 banks: the row-per-lane 16-byte loads of
+                                     // the diagonal chains are conflict-free (pitch 68: 8-way), the 4-lanes-per-row products 2-way
+constexpr int TILE_DOUBLES = SB64 * TP;
+__host__ __device__ __forceinline__ size_t ktile_base(int tr, int tc) { return (size_t)(tr * (tr + 1) / 2 + tc) * TILE_DOUBLES; }
+__device__ __forceinline__ size_t kidx(int row, int col) {
+  return ktile_base(row >> 6, col >> 6) + (size_t)((row & 63) * TP + (col & 63));
+}
 
 struct FusedArgs {
   View v;
@@ -72,11 +88,10 @@ struct FusedArgs {
   // streamed solve (ipmz_batch_solve_streamed): the kernel is launched BEFORE the problem data is uploaded; `ready` is a
   // device word the copy stream overwrites (4-byte H2D copy, stream-ordered after each chunk of problems) with the number
   // of problems whose data is resident.  A CTA holding ticket p waits until *ready > p, then builds the reference's
-  // initial point and the transposed copy M^T itself (the upload path's k_initial_point / k_transpose could not be
+  // initial point itself (the upload path's k_initial_point could not be
   // scheduled while this persistent grid owns every SM).  nullptr: everything is resident already.
   const volatile int* ready;
   int* abort_flag;   // set when a wait on `ready` times out (the host returns an error instead of hanging the GPU)
-  double* MT_w;      // writable alias of v.MT for the in-kernel transpose
   int dbg;  // experiments (IPMZ_FUSED_DBG): 1 = only the opening matvecs (30x), 2 = assembly (20x), 3 = + LDL^T, 4 = + one solve
 };
 
@@ -112,48 +127,7 @@ __device__ __forceinline__ void cta_reduce(double (&v)[K], double (*red)[FW], do
   }
 }
 
-// y[r] = dot(A[r][0:cols], x), one warp per row, four rows in flight per warp (the rows are 1-2 KB: a single row per
-// trip leaves the warp waiting on one L2 / HBM round trip).  Per row the accumulation order is that of
-// k_matvec_short (two accumulators by trip parity, then the shuffle tree).
-__device__ __forceinline__ void cta_matvec(const double* __restrict__ A, int lda, int rows, int cols, const double* x,
-                                           double* y) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c2 = (cols + 1) >> 1;
-  const double2* x2 = reinterpret_cast<const double2*>(x);
-  for (int r0 = warp * 4; r0 < rows; r0 += FW * 4) {
-    double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
-    const double2* a2[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) a2[u] = reinterpret_cast<const double2*>(A + (size_t)min(r0 + u, rows - 1) * lda);
-    int k = lane;
-    for (; k + 32 < c2; k += 64) {
-      double2 a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = a2[u][k]; b[u] = a2[u][k + 32]; }
-      const double2 xa = x2[k], xb = x2[k + 32];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc0[u] = fma(a[u].x, xa.x, acc0[u]); acc0[u] = fma(a[u].y, xa.y, acc0[u]);
-        acc1[u] = fma(b[u].x, xb.x, acc1[u]); acc1[u] = fma(b[u].y, xb.y, acc1[u]);
-      }
-    }
-    for (; k < c2; k += 32) {
-      const double2 xa = x2[k];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double2 a = a2[u][k];
-        acc0[u] = fma(a.x, xa.x, acc0[u]); acc0[u] = fma(a.y, xa.y, acc0[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double s = wsum(acc0[u] + acc1[u]);
-      if (lane == 0 && r0 + u < rows) y[r0 + u] = s;
-    }
-  }
-}
-
-// Matrix-vector product, TMA version (default; -DIPMZ_FUSED_NO_TMA_MV selects cta_matvec above): the matrix (rows contiguous, pitch lda) streams through
+// Matrix-vector product: the matrix (rows contiguous, pitch lda) streams through
 // two 32 KB shared-memory buffers by bulk copies (cp.async.bulk.shared.global, SASS UBLKCP): ONE instruction of one
 // thread moves a whole chunk and completes on an mbarrier by transaction bytes.  Work split inside a chunk: S = 2^k
 // lanes share one row (S >= cols / 16, so a lane's part of x is 8 double2 registers loaded once per call), FT / S rows
@@ -163,51 +137,109 @@ constexpr int MV_NBUF = 2;
 constexpr int MV_CHUNK = 4096;  // doubles per staging buffer
 __shared__ __align__(8) unsigned long long g_mvbar[MV_NBUF];  // one mbarrier per staging buffer, initialised by the kernel
 __shared__ unsigned g_mvph;                                    // their phase bits (uniform per CTA)
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+// L2 eviction priorities (createpolicy): the working set of the problems in flight (Q, M and K of 296 problems: 370 MB)
+// is three times the L2.  M is re-read 7 to 13 times per iteration, Q 1.5 to 3.5 times: M's lines are kept
+// (evict_last), Q's are marked evict_first so that streaming Q does not push M and the factor out.
+// IPMZ_L2_HINTS=0 (compile time) builds without the hints for A/B runs.
+#ifndef IPMZ_L2_HINTS
+#define IPMZ_L2_HINTS 0
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+enum { L2_NORMAL = 0, L2_KEEP = 1, L2_STREAM = 2 };
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar,
+                                          int hint = L2_NORMAL) {
   const unsigned da = (unsigned)__cvta_generic_to_shared(smem_dst);
   const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
   // earlier generic-proxy accesses of the buffer (other phases use the same shared memory) before the async-proxy write
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
+#if IPMZ_L2_HINTS
+  if (hint != L2_NORMAL) {
+    const unsigned long long pol = hint == L2_KEEP ? l2_policy_evict_last() : l2_policy_evict_first();
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(da), "l"(gsrc), "r"(bytes), "r"(ba), "l"(pol) : "memory");
+    return;
+  }
+#endif
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(da), "l"(gsrc), "r"(bytes), "r"(ba) : "memory");
 }
-// bar: MV_NBUF mbarriers (count 1) initialised once per kernel; ph: their phase bits, carried by the caller
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, int src_bytes, unsigned long long pol) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+#if IPMZ_L2_HINTS
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(sa), "l"(gsrc), "r"(src_bytes), "l"(pol));
+#else
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(src_bytes));
+#endif
+}
+__device__ __forceinline__ double2 ld_stream2(const double* p) {  // 16-byte load, L2 evict_first
+#if IPMZ_L2_HINTS
+  double2 r;
+  const unsigned long long pol = l2_policy_evict_first();
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+  return r;
+#else
+  return *reinterpret_cast<const double2*>(p);
+#endif
+}
+// bar: MV_NBUF mbarriers (count 1) initialised once per kernel; ph: their phase bits, carried by the caller.
+// ROWDOT: y[r] = dot(A[r][0:cols], x) (above).  COLACC: yt[j] = sum_r A[r][j] vt[r] from the SAME staged chunk -- thread j
+// owns column j (and j + FT), four accumulators by r mod 4, conflict-free reads -- so M^T v needs no transposed copy of
+// M and the opening M x / M^T lambda of an iteration are ONE pass over M.
+template <bool ROWDOT, bool COLACC>
 __device__ __noinline__ void cta_matvec_tma(const double* __restrict__ A, int lda, int rows, int cols, const double* x,
-                                            double* y, double* sm) {
+                                            double* y, const double* vt, double* yt, double* sm, int hint) {
   const int tid = threadIdx.x;
   unsigned long long* bar = g_mvbar;
   const int c2 = (cols + 1) >> 1;
   int S = 4;
   while (8 * S < c2) S <<= 1;  // cols <= 512 -> S <= 32
-  int R = FT / S;              // rows per chunk
+  int R = ROWDOT ? FT / S : MV_CHUNK / lda;  // rows per chunk
   if (R * lda > MV_CHUNK) R = MV_CHUNK / lda;
+  if (COLACC) R &= ~3;  // chunks start at multiples of four rows (16-byte reads of the staged vector); R >= 8
   const int nch = (rows + R - 1) / R;
   const int rr = tid / S, seg = tid - rr * S;
+  const bool exact = c2 == 8 * S;  // every lane's eight column pairs exist (cfg4: 256 columns, 16 lanes per row)
+  double* svt = sm + MV_NBUF * MV_CHUNK;  // COLACC: vt staged in shared memory (broadcast reads in the inner loop)
   __syncthreads();  // the staging buffers are free and x is visible
   unsigned ph = g_mvph;
   if (tid == 0)
     for (int c = 0; c < MV_NBUF && c < nch; ++c)
-      bulk_load(sm + c * MV_CHUNK, A + (size_t)c * R * lda, (unsigned)(min(R, rows - c * R) * lda) * 8u, bar + c);
+      bulk_load(sm + c * MV_CHUNK, A + (size_t)c * R * lda, (unsigned)(min(R, rows - c * R) * lda) * 8u, bar + c, hint);
   double2 xr[8];
+  if (ROWDOT) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = seg + S * j;
-    xr[j] = k < c2 ? reinterpret_cast<const double2*>(x)[k] : make_double2(0.0, 0.0);
+    for (int j = 0; j < 8; ++j) {
+      const int k = seg + S * j;
+      xr[j] = (exact || k < c2) ? reinterpret_cast<const double2*>(x)[k] : make_double2(0.0, 0.0);
+    }
   }
+  if (COLACC) {
+    for (int i = tid; i < ((rows + 3) & ~3); i += FT) svt[i] = i < rows ? vt[i] : 0.0;
+    __syncthreads();
+  }
+  double ca[4] = {0.0, 0.0, 0.0, 0.0}, cb[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool col_a = tid < cols, col_b = tid + FT < cols;
   for (int c = 0; c < nch; ++c) {
     const int bi = c % MV_NBUF;
     mbar_wait(bar + bi, (ph >> bi) & 1u);
     ph ^= 1u << bi;
     const int r0 = c * R, nr = min(R, rows - r0);
-    {
-      const double2* a2 = reinterpret_cast<const double2*>(sm + bi * MV_CHUNK + (size_t)(rr < nr ? rr : 0) * lda);
+    const double* buf = sm + bi * MV_CHUNK;
+    if (ROWDOT) {
+      const double2* a2 = reinterpret_cast<const double2*>(buf + (size_t)(rr < nr ? rr : 0) * lda) + seg;
       double2 av[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = seg + S * j;
-        av[j] = k < c2 ? a2[k] : make_double2(0.0, 0.0);
-      }
+      for (int j = 0; j < 8; ++j) av[j] = (exact || seg + S * j < c2) ? a2[S * j] : make_double2(0.0, 0.0);
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
@@ -215,24 +247,64 @@ __device__ __noinline__ void cta_matvec_tma(const double* __restrict__ A, int ld
         acc2 = fma(av[j + 1].x, xr[j + 1].x, acc2); acc3 = fma(av[j + 1].y, xr[j + 1].y, acc3);
       }
       double t = (acc0 + acc1) + (acc2 + acc3);
-      for (int o = S >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (S >= 32) t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (S >= 16) t += __shfl_xor_sync(0xffffffffu, t, 8);
+      if (S >= 8) t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
       if (seg == 0 && rr < nr) y[r0 + rr] = t;
+    }
+    if (COLACC && col_a) {
+      // accumulator u takes the rows r0 + r + u of every group of four (static indexing: a dynamically indexed
+      // accumulator array would live in local memory); rows past `rows` are zeros in svt and stale (finite or not,
+      // times zero is avoided by the bound) data in the buffer
+      const double* sa = buf + tid;
+      const double* sv = svt + r0;
+      const int n4 = nr & ~3;
+      for (int r = 0; r < n4; r += 4) {
+        const double2 v01 = *reinterpret_cast<const double2*>(sv + r), v23 = *reinterpret_cast<const double2*>(sv + r + 2);
+        ca[0] = fma(sa[(size_t)r * lda], v01.x, ca[0]);
+        ca[1] = fma(sa[(size_t)(r + 1) * lda], v01.y, ca[1]);
+        ca[2] = fma(sa[(size_t)(r + 2) * lda], v23.x, ca[2]);
+        ca[3] = fma(sa[(size_t)(r + 3) * lda], v23.y, ca[3]);
+        if (col_b) {
+          cb[0] = fma(sa[(size_t)r * lda + FT], v01.x, cb[0]);
+          cb[1] = fma(sa[(size_t)(r + 1) * lda + FT], v01.y, cb[1]);
+          cb[2] = fma(sa[(size_t)(r + 2) * lda + FT], v23.x, cb[2]);
+          cb[3] = fma(sa[(size_t)(r + 3) * lda + FT], v23.y, cb[3]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (n4 + u < nr) {
+          ca[u] = fma(sa[(size_t)(n4 + u) * lda], sv[n4 + u], ca[u]);
+          if (col_b) cb[u] = fma(sa[(size_t)(n4 + u) * lda + FT], sv[n4 + u], cb[u]);
+        }
     }
     __syncthreads();
     if (tid == 0 && c + MV_NBUF < nch)
       bulk_load(sm + bi * MV_CHUNK, A + (size_t)(c + MV_NBUF) * R * lda,
-                (unsigned)(min(R, rows - (c + MV_NBUF) * R) * lda) * 8u, bar + bi);
+                (unsigned)(min(R, rows - (c + MV_NBUF) * R) * lda) * 8u, bar + bi, hint);
+  }
+  if (COLACC) {
+    if (col_a) yt[tid] = (ca[0] + ca[1]) + (ca[2] + ca[3]);
+    if (col_b) yt[tid + FT] = (cb[0] + cb[1]) + (cb[2] + cb[3]);
   }
   if (tid == 0) g_mvph = ph;  // read by the next call after its opening barrier
 }
-#ifndef IPMZ_FUSED_NO_TMA_MV
-#define MATVEC(A_, lda_, rows_, cols_, x_, y_) cta_matvec_tma(A_, lda_, rows_, cols_, x_, y_, sm)
-#else
-#define MATVEC(A_, lda_, rows_, cols_, x_, y_) cta_matvec(A_, lda_, rows_, cols_, x_, y_)
-#endif
+#define MATVEC(A_, lda_, rows_, cols_, x_, y_) cta_matvec_tma<true, false>(A_, lda_, rows_, cols_, x_, y_, nullptr, nullptr, sm, L2_KEEP)
+// the same for Q (streamed: evict_first)
+#define MATVEC_Q(A_, lda_, rows_, cols_, x_, y_) cta_matvec_tma<true, false>(A_, lda_, rows_, cols_, x_, y_, nullptr, nullptr, sm, L2_STREAM)
+// yt = A^T vt (A stored by rows)
+#define MATVEC_T(A_, lda_, rows_, cols_, vt_, yt_) cta_matvec_tma<false, true>(A_, lda_, rows_, cols_, nullptr, nullptr, vt_, yt_, sm, L2_KEEP)
+// y = A x and yt = A^T vt in one pass over A
+#define MATVEC_BOTH(A_, lda_, rows_, cols_, x_, y_, vt_, yt_) cta_matvec_tma<true, true>(A_, lda_, rows_, cols_, x_, y_, vt_, yt_, sm, L2_KEEP)
 
 // ---- assembly ---------------------------------------------------------------------------------------------------
-// NORMAL: K(lower) = Q + diag(hd) + MT diag(w) MT^T, hd = Y^-1 L_y + Z^-1 L_z.  sm: FSTAGES stages | w[ms] | hd[ns].
+// NORMAL: K(lower) = Q + diag(hd) + M^T diag(w) M, hd = Y^-1 L_y + Z^-1 L_z.  sm: FSTAGES stages | w[ms] | hd[ns].
+// The operands are 16-row slices of M itself (rows = constraints = the contraction index): a stage holds the 64 columns
+// of the tile's row block and the 64 columns of its column block, [k][i] with pitch 68, and the DMMA fragments are read
+// down the columns -- no transposed copy of M exists in the fused path.
 __device__ void assemble_normal(const View& v, int p, double* sm) {
   const Shape& s = v.s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -242,7 +314,7 @@ __device__ void assemble_normal(const View& v, int p, double* sm) {
   double* hd = wsm + s.ms;
   const double* V = v.V + (size_t)p * v.sp;
   const double* Q = v.Q + (size_t)p * v.sQ;
-  const double* MT = v.MT + (size_t)p * v.sMT;
+  const double* M = v.M + (size_t)p * v.sM;
   double* K = v.K + (size_t)p * v.sK;
   for (int i = tid; i < s.ms; i += FT) wsm[i] = i < s.m ? v.W[(size_t)p * s.ms + i] : 0.0;
   for (int i = tid; i < s.n; i += FT) {
@@ -256,19 +328,23 @@ __device__ void assemble_normal(const View& v, int p, double* sm) {
   const int ntile = nt * (nt + 1) / 2;
   const int nsteps = ntile * KT;
 
-  // load cursor (runs FSTAGES-1 steps ahead of the compute cursor, across tile boundaries)
+  // load cursor (runs FSTAGES-1 steps ahead of the compute cursor, across tile boundaries).  A thread's four 16-byte
+  // chunks of a stage: rows lrow and lrow + 8 of the slice, A side (tile row block) and B side (tile column block).
   int l_ti = 0, l_tj = 0, l_kt = 0;
+  const int lrow = tid >> 5, lck = (tid & 31) * 2;
+  const int ldm = v.ldm, m = s.m, ns = s.ns, n = s.n;
+  const unsigned sm_u = (unsigned)__cvta_generic_to_shared(sm) + (unsigned)(lrow * PA + lck) * 8u;
   auto load_next = [&](int stage) {
-    double* As = sm + stage * STAGE_DOUBLES;
-    const int kbase = l_kt * BK;
+    const unsigned dst = sm_u + (unsigned)(stage * STAGE_DOUBLES) * 8u;
+    const int k0 = l_kt * BK + lrow;
+    const int ca = l_ti * TS + lck, cb = l_tj * TS + lck;
 #pragma unroll
-    for (int i = 0; i < 2 * TS * (BK / 2) / FT; ++i) {
-      const int chunk = tid + i * FT;
-      const int r = chunk >> 3, ck = (chunk & 7) * 2;
-      const int gr = (r < TS ? l_ti * TS + r : l_tj * TS + (r - TS));
-      const int k = kbase + ck;
-      const bool ok = gr < s.n && k < s.ms;  // MT's padding columns [m, ms) are zero
-      cp_async16(As + r * LDT + ck, MT + (size_t)(ok ? gr : 0) * v.ldmt + (ok ? k : 0), ok ? 16 : 0);
+    for (int h = 0; h < 2; ++h) {
+      const int k = k0 + 8 * h;
+      const double* row = M + (size_t)(k < m ? k : 0) * ldm;
+      const bool oka = k < m && ca < ns, okb = k < m && cb < ns;  // M's padding columns [n, ns) are zero
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + (unsigned)(8 * h * PA) * 8u), "l"(row + (oka ? ca : 0)), "r"(oka ? 16 : 0));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + (unsigned)((BK + 8 * h) * PA) * 8u), "l"(row + (okb ? cb : 0)), "r"(okb ? 16 : 0));
     }
     if (++l_kt == KT) { l_kt = 0; if (++l_tj > l_ti) { l_tj = 0; ++l_ti; } }
   };
@@ -278,65 +354,64 @@ __device__ void assemble_normal(const View& v, int p, double* sm) {
     if (loaded < nsteps) load_next(loaded);
     cp_async_commit();
   }
-  int ti = 0, tj = 0;
-  double acc[4][2][2];
-  for (int step = 0, kt = 0; step < nsteps; ++step) {
-    const int row0 = ti * TS + wm * 32, col0 = tj * TS + wn * 16;
-    if (kt == 0) {
+  int stage = 0;
+  for (int ti = 0; ti < nt; ++ti)
+    for (int tj = 0; tj <= ti; ++tj) {
+      const int row0 = ti * TS + wm * 32 + g, col0 = tj * TS + wn * 16 + 2 * q;
+      double acc[4][2][2];
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
-        const int row = row0 + mi * 8 + g;
+        const int row = row0 + mi * 8;
 #pragma unroll
         for (int ni = 0; ni < 2; ++ni) {
-          const int col = col0 + ni * 8 + 2 * q;
+          const int col = col0 + ni * 8;
           double2 c = make_double2(0.0, 0.0);
-          if (row < s.n && col < s.ns) c = *reinterpret_cast<const double2*>(Q + (size_t)row * v.ldq + col);
-          if (row == col) c.x += hd[row < s.n ? row : 0];
-          if (row == col + 1) c.y += hd[row < s.n ? row : 0];
+          if (row < n && col < ns) c = *reinterpret_cast<const double2*>(Q + (size_t)row * v.ldq + col);
+          if (row == col) c.x += hd[row < n ? row : 0];
+          if (row == col + 1) c.y += hd[row < n ? row : 0];
           acc[mi][ni][0] = c.x; acc[mi][ni][1] = c.y;
         }
       }
-    }
-    cp_async_wait<FSTAGES - 2>();
-    __syncthreads();
-    if (loaded < nsteps) load_next(loaded % FSTAGES);
-    cp_async_commit();
-    ++loaded;
-    const double* As = sm + (step % FSTAGES) * STAGE_DOUBLES;
-    const double* Aw = As + (wm * 32 + g) * LDT + q;
-    const double* Bw = As + (TS + wn * 16 + g) * LDT + q;
-    const double* wk = wsm + kt * BK + q;
+#pragma unroll 1
+      for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<FSTAGES - 2>();
+        __syncthreads();
+        if (loaded < nsteps) load_next(loaded % FSTAGES);
+        cp_async_commit();
+        ++loaded;
+        const double* As = sm + stage * STAGE_DOUBLES;
+        if (++stage == FSTAGES) stage = 0;
+        const double* Aw = As + q * PA + wm * 32 + g;
+        const double* Bw = As + (BK + q) * PA + wn * 16 + g;
+        const double* wk = wsm + kt * BK + q;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double af[4], bf[2];
-      const double w = wk[kk * 4];
+        for (int kk = 0; kk < BK / 4; ++kk) {
+          double af[4], bf[2];
+          const double w = wk[kk * 4];
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) af[mi] = Aw[mi * 8 * LDT + kk * 4];
+          for (int mi = 0; mi < 4; ++mi) af[mi] = Aw[kk * 4 * PA + mi * 8];
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) bf[ni] = Bw[ni * 8 * LDT + kk * 4] * w;
+          for (int ni = 0; ni < 2; ++ni) bf[ni] = Bw[kk * 4 * PA + ni * 8] * w;
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+          for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
-    }
-    if (++kt == KT) {
-      kt = 0;
+            for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], af[mi], bf[ni]);
+        }
+      }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi) {
-        const int row = row0 + mi * 8 + g;
-        if (row >= s.n) continue;
+        const int row = row0 + mi * 8;
+        if (row >= n) continue;
 #pragma unroll
         for (int ni = 0; ni < 2; ++ni) {
-          const int col = col0 + ni * 8 + 2 * q;
+          const int col = col0 + ni * 8;
           if (col > row) continue;
-          double* dst = K + (size_t)row * v.ldk + col;
+          double* dst = K + kidx(row, col);
           if (col + 1 <= row) *reinterpret_cast<double2*>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
           else dst[0] = acc[mi][ni][0];
         }
       }
-      if (++tj > ti) { tj = 0; ++ti; }
     }
-  }
   cp_async_wait<0>();
   __syncthreads();
 }
@@ -348,31 +423,30 @@ __device__ void assemble_augmented(const View& v, int p) {
   const double* V = v.V + (size_t)p * v.sp;
   double* K = v.K + (size_t)p * v.sK;
   for (int r = warp; r < v.N; r += FW) {
-    double* Kr = K + (size_t)r * v.ldk;
     if (r < s.n) {
       const double* q = v.Q + (size_t)p * v.sQ + (size_t)r * v.ldq;
-      for (int c = lane; c < r; c += 32) Kr[c] = q[c];
+      for (int c = lane; c < r; c += 32) K[kidx(r, c)] = q[c];
       if (lane == 0) {
         double dii = q[r];
         if (s.ylo) dii = dii + inv_guard(nslot(V, s, YS)[r]) * nslot(V, s, LAMY)[r];
         if (s.zup) dii = dii + inv_guard(nslot(V, s, ZS)[r]) * nslot(V, s, LAMZ)[r];
-        Kr[r] = dii;
+        K[kidx(r, r)] = dii;
       }
     } else {
       const int j = r - s.n;
       const double* mr = v.M + (size_t)p * v.sM + (size_t)j * v.ldm;
-      for (int c = lane; c < s.n; c += 32) Kr[c] = mr[c];
-      for (int c = s.n + lane; c < r; c += 32) Kr[c] = 0.0;
-      if (lane == 0) Kr[r] = -v.winv[(size_t)p * s.ms + j];
+      for (int c = lane; c < s.n; c += 32) K[kidx(r, c)] = mr[c];
+      for (int c = s.n + lane; c < r; c += 32) K[kidx(r, c)] = 0.0;
+      if (lane == 0) K[kidx(r, r)] = -v.winv[(size_t)p * s.ms + j];
     }
   }
   __syncthreads();
 }
 
 // ---- factorization ----------------------------------------------------------------------------------------------
-// In place on the lower triangle of K (N x N, leading dimension ld): strict lower = L, pivots -> Dg.
+// In place on the lower triangle of K (N x N, tile-major: kidx): strict lower = L, pivots -> Dg.
 // sm: panel [round16(N) x PP] | dsm[32] | dinv[32] | colbuf[CBUF] | binv[INV_SUB].
-__device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
+__device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int rows_cap = (N + 15) & ~15;
@@ -390,7 +464,7 @@ __device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
       const int r = idx >> 4, c = (idx & 15) * 2;
       int bytes = 0;
       if (r < R && c < jb && !(r < jb && c > r)) bytes = (jb - c >= 2) ? 16 : 8;
-      cp_async16(P + r * PP + c, K + (size_t)(j0 + (bytes ? r : 0)) * ld + j0 + (bytes ? c : 0), bytes);
+      cp_async16(P + r * PP + c, K + kidx(j0 + (bytes ? r : 0), j0 + (bytes ? c : 0)), bytes);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -406,22 +480,24 @@ __device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
     // ---- L and the pivots back to global memory
     for (int idx = tid; idx < R * SB; idx += FT) {
       const int r = idx >> 5, c = idx & 31;
-      if (c < jb && (r >= jb || c < r)) K[(size_t)(j0 + r) * ld + j0 + c] = P[r * PP + c];
+      if (c < jb && (r >= jb || c < r)) K[kidx(j0 + r, j0 + c)] = P[r * PP + c];
     }
     if (tid < jb) Dg[j0 + tid] = dsm[tid];
     // ---- trailing update  C -= L_panel diag(d) L_panel^T  on the lower triangle, 16 x 16 tiles per warp
     if (rem > 0) {
       const double* T = P + SB * PP;
-      double* C = K + (size_t)(j0 + SB) * ld + (j0 + SB);
+      const int t0 = j0 + SB;  // first row / column of the trailing matrix
       const int tm = (rem + 15) >> 4;
       const int ntask = tm * (tm + 1) / 2;
-      for (int t = warp; t < ntask; t += FW) {
-        int mi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      // the C values of a warp's NEXT tile are requested before the DMMAs of the current one (the trailing matrix
+      // lives in L2: a tile loaded on demand would expose one L2 round trip per 32 DMMAs)
+      auto tile_of = [&](int t, int& mi, int& ni) {
+        mi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
         while (mi * (mi + 1) / 2 > t) --mi;
         while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
-        const int ni = t - mi * (mi + 1) / 2;
-        const int ra = mi * 16 + g, rb = ni * 16 + g;
-        double2 cv[2][2];
+        ni = t - mi * (mi + 1) / 2;
+      };
+      auto load_c = [&](int mi, int ni, double2 (&cv)[2][2]) {
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -429,27 +505,46 @@ __device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
             const int row = mi * 16 + i * 8 + g, col = ni * 16 + j * 8 + 2 * q;
             cv[i][j] = make_double2(0.0, 0.0);
             if (row < rem && col <= row) {
-              const double* src = C + (size_t)row * ld + col;
+              const double* src = K + kidx(t0 + row, t0 + col);
               if (col + 1 <= row) cv[i][j] = *reinterpret_cast<const double2*>(src);
               else cv[i][j].x = src[0];
             }
           }
-        double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
-        double af[8][2], bf[8][2];
+      };
+      double2 cvn[2][2];
+      int mi_n = 0, ni_n = 0;
+      if (warp < ntask) { tile_of(warp, mi_n, ni_n); load_c(mi_n, ni_n, cvn); }
+      for (int t = warp; t < ntask; t += FW) {
+        const int mi = mi_n, ni = ni_n;
+        // accumulators start from C and take the products with the sign folded into the B fragment (the reference's own
+        // order: sum -= L[j][k] * L[i][k] * D[k], LinearSolvers.cpp:32-34); k in two halves of 16 keeps the fragment
+        // registers at 16 doubles (a full set of 32 next to the prefetched tile spilled the accumulators)
+        double acc[2][2][2];
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          const double dk = dsm[k8 * 4 + q];
-          af[k8][0] = T[ra * PP + k8 * 4 + q];
-          af[k8][1] = T[(ra + 8) * PP + k8 * 4 + q];
-          bf[k8][0] = T[rb * PP + k8 * 4 + q] * dk;
-          bf[k8][1] = T[(rb + 8) * PP + k8 * 4 + q] * dk;
-        }
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-          dmma884(acc[0][0], af[k8][0], bf[k8][0]);
-          dmma884(acc[0][1], af[k8][0], bf[k8][1]);
-          dmma884(acc[1][0], af[k8][1], bf[k8][0]);
-          dmma884(acc[1][1], af[k8][1], bf[k8][1]);
+          for (int j = 0; j < 2; ++j) { acc[i][j][0] = cvn[i][j].x; acc[i][j][1] = cvn[i][j].y; }
+        if (t + FW < ntask) { tile_of(t + FW, mi_n, ni_n); load_c(mi_n, ni_n, cvn); }
+        const int ra = mi * 16 + g, rb = ni * 16 + g;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          double af[4][2], bf[4][2];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kk = (kh * 4 + k4) * 4 + q;
+            const double dk = -dsm[kk];
+            af[k4][0] = T[ra * PP + kk];
+            af[k4][1] = T[(ra + 8) * PP + kk];
+            bf[k4][0] = T[rb * PP + kk] * dk;
+            bf[k4][1] = T[(rb + 8) * PP + kk] * dk;
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            dmma884(acc[0][0], af[k4][0], bf[k4][0]);
+            dmma884(acc[0][1], af[k4][0], bf[k4][1]);
+            dmma884(acc[1][0], af[k4][1], bf[k4][0]);
+            dmma884(acc[1][1], af[k4][1], bf[k4][1]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -457,9 +552,9 @@ __device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
           for (int j = 0; j < 2; ++j) {
             const int row = mi * 16 + i * 8 + g, col = ni * 16 + j * 8 + 2 * q;
             if (row < rem && col <= row) {
-              double* dst = C + (size_t)row * ld + col;
-              if (col + 1 <= row) *reinterpret_cast<double2*>(dst) = make_double2(cv[i][j].x - acc[i][j][0], cv[i][j].y - acc[i][j][1]);
-              else dst[0] = cv[i][j].x - acc[i][j][0];
+              double* dst = K + kidx(t0 + row, t0 + col);
+              if (col + 1 <= row) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+              else dst[0] = acc[i][j][0];
             }
           }
       }
@@ -470,100 +565,247 @@ __device__ void ldlt_panels(double* K, int ld, double* Dg, int N, double* sm) {
 
 // ---- solves -----------------------------------------------------------------------------------------------------
 // x <- L^-1 x, x <- x / D, x <- L^-T x with the in-place factor; x (global, length N) is staged in shared memory.
-// sm: sx[nblk * 64] | Ld[64 x 65] | part[4][64].
-__device__ void ldlt_solve(const double* K, int ld, const double* Dg, int N, double* x, double* sm) {
+// The factor is consumed as 64 x 64 tiles in ONE fixed sequence -- forward (0,0) (1,0) (1,1) (2,0) ... (b,b), then the
+// same tiles in reverse order for the transposed sweep -- through a 3-stage cp.async ring that runs two tiles ahead of
+// the arithmetic across block-row and sweep boundaries: the only exposed memory round trip of a solve is the first one
+// (the previous version loaded every diagonal block and every off-diagonal strip on demand: 16 exposed L2 / HBM
+// latencies per solve).  Off-diagonal tiles are 64 x 64 matrix-vector products over all 256 threads (4 lanes per row /
+// column, shuffle reduction); a diagonal tile is the substitution chain of one warp, four columns per step.
+// sm: sx[nblk * 64] | SOLVE_STAGES tiles [64 x TP].
+#ifndef IPMZ_SOLVE_STAGES
+#define IPMZ_SOLVE_STAGES 2
+#endif
+constexpr int SOLVE_STAGES = IPMZ_SOLVE_STAGES;
+// position in the tile sequence: forward (0,0) (1,0) (1,1) (2,0) ..., the last tile twice, then the same way back
+struct TileCursor {
+  int r = 0, c = 0;
+  __device__ __forceinline__ void advance(int k, int ntile) {  // from step k to step k + 1
+    if (k + 1 < ntile) { if (c < r) ++c; else { ++r; c = 0; } }
+    else if (k + 1 > ntile) { if (c > 0) --c; else { --r; c = r; } }
+  }
+};
+
+__shared__ __align__(8) unsigned long long g_svbar[4];  // one mbarrier per ring stage (SOLVE_STAGES <= 4)
+__shared__ unsigned g_svph;                             // their phase bits
+
+// Tile (r, c) of the factor -> stage: ONE bulk copy (cp.async.bulk, 35 KB contiguous in the tile-major layout) that
+// completes on the stage's mbarrier by transaction bytes.
+__device__ __forceinline__ void solve_tile_issue(double* stage, unsigned long long* bar, const double* K, int r, int c) {
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(stage);
+  constexpr unsigned bytes = TILE_DOUBLES * 8u;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;\n" ::"r"(ba), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(sa), "l"(K + ktile_base(r, c)), "r"(bytes), "r"(ba) : "memory");
+}
+
+struct TriFwd { double l10, l20, l21, l30, l31, l32; double2 a01, a23, b01, b23; };
+__device__ __forceinline__ void tri64_forward_load(TriFwd& k, const double* T, int b, const double* r0, const double* r1) {
+  const int c0 = 4 * b;
+  const double* d = T + c0 * TP + c0;
+  k.l10 = d[TP]; k.l20 = d[2 * TP]; k.l21 = d[2 * TP + 1];
+  k.l30 = d[3 * TP]; k.l31 = d[3 * TP + 1]; k.l32 = d[3 * TP + 2];
+  k.a01 = *reinterpret_cast<const double2*>(r0 + c0); k.a23 = *reinterpret_cast<const double2*>(r0 + c0 + 2);
+  k.b01 = *reinterpret_cast<const double2*>(r1 + c0); k.b23 = *reinterpret_cast<const double2*>(r1 + c0 + 2);
+}
+template <bool HI>
+__device__ __forceinline__ void tri64_forward_block(const TriFwd& k, int b, double& y0, double& y1, int lane) {
+  const int c0 = 4 * b;
+  const double src = HI ? y1 : y0;
+  const double v0 = __shfl_sync(0xffffffffu, src, (c0 + 0) & 31);
+  const double v1 = __shfl_sync(0xffffffffu, src, (c0 + 1) & 31);
+  const double v2 = __shfl_sync(0xffffffffu, src, (c0 + 2) & 31);
+  const double v3 = __shfl_sync(0xffffffffu, src, (c0 + 3) & 31);
+  const double x0 = v0;
+  const double x1 = fma(-k.l10, x0, v1);
+  const double x2 = fma(-k.l21, x1, fma(-k.l20, x0, v2));
+  const double x3 = fma(-k.l32, x2, fma(-k.l31, x1, fma(-k.l30, x0, v3)));
+  const double xs = (lane & 3) == 0 ? x0 : (lane & 3) == 1 ? x1 : (lane & 3) == 2 ? x2 : x3;  // c0 is a multiple of 4
+  if (!HI) {
+    const double u0 = fma(-k.a23.y, x3, fma(-k.a23.x, x2, fma(-k.a01.y, x1, fma(-k.a01.x, x0, y0))));
+    y0 = lane >= c0 + 4 ? u0 : (lane >= c0 ? xs : y0);
+    y1 = fma(-k.b23.y, x3, fma(-k.b23.x, x2, fma(-k.b01.y, x1, fma(-k.b01.x, x0, y1))));
+  } else {
+    const int rr = lane + 32;
+    const double u1 = fma(-k.b23.y, x3, fma(-k.b23.x, x2, fma(-k.b01.y, x1, fma(-k.b01.x, x0, y1))));
+    y1 = rr >= c0 + 4 ? u1 : (rr >= c0 ? xs : y1);
+  }
+}
+// Rolled loops on purpose (one warp's dependent chain, run once per tile: straight-line code of 16 blocks is fetched
+// cold from the instruction cache every time); the coefficients of block b + 1 are loaded before block b's chain, and
+// the in-block rows are selected, not branched (tools/tri_probe.cu: 2500 cycles per tile against 3500 for the
+// per-column chain, bitwise the same values; pitch 70 makes the row-per-lane 16-byte loads conflict-free).
+__device__ __forceinline__ void tri64_forward(const double* T, double* y, int lane) {
+  double y0 = y[lane], y1 = y[lane + 32];
+  const double* r0 = T + lane * TP;
+  const double* r1 = T + (lane + 32) * TP;
+  TriFwd ka, kb;
+  tri64_forward_load(ka, T, 0, r0, r1);
+#pragma unroll 1
+  for (int b = 0; b < 8; b += 2) {
+    tri64_forward_load(kb, T, b + 1, r0, r1);
+    tri64_forward_block<false>(ka, b, y0, y1, lane);
+    tri64_forward_load(ka, T, b + 2, r0, r1);
+    tri64_forward_block<false>(kb, b + 1, y0, y1, lane);
+  }
+#pragma unroll 1
+  for (int b = 8; b < 16; b += 2) {
+    tri64_forward_load(kb, T, b + 1, r0, r1);
+    tri64_forward_block<true>(ka, b, y0, y1, lane);
+    tri64_forward_load(ka, T, b + 2 < 16 ? b + 2 : 15, r0, r1);
+    tri64_forward_block<true>(kb, b + 1, y0, y1, lane);
+  }
+  y[lane] = y0;
+  y[lane + 32] = y1;
+}
+
+// the transposed (unit upper triangular) solve with the same tile: rows 63 .. 0, four at a time
+struct TriBwd { double l10, l20, l21, l30, l31, l32, a0, a1, a2, a3, b0, b1, b2, b3; };
+__device__ __forceinline__ void tri64_backward_load(TriBwd& k, const double* T, int b, int lane) {
+  const int c0 = 4 * b;
+  const double* d = T + c0 * TP + c0;
+  k.l10 = d[TP]; k.l20 = d[2 * TP]; k.l21 = d[2 * TP + 1];
+  k.l30 = d[3 * TP]; k.l31 = d[3 * TP + 1]; k.l32 = d[3 * TP + 2];
+  const double* c = T + c0 * TP + lane;
+  k.a0 = c[0]; k.a1 = c[TP]; k.a2 = c[2 * TP]; k.a3 = c[3 * TP];
+  k.b0 = c[32]; k.b1 = c[TP + 32]; k.b2 = c[2 * TP + 32]; k.b3 = c[3 * TP + 32];  // used for c0 > 32 only
+}
+template <bool HI>
+__device__ __forceinline__ void tri64_backward_block(const TriBwd& k, int b, double& y0, double& y1, int lane) {
+  const int c0 = 4 * b;
+  const double src = HI ? y1 : y0;
+  const double v0 = __shfl_sync(0xffffffffu, src, (c0 + 0) & 31);
+  const double v1 = __shfl_sync(0xffffffffu, src, (c0 + 1) & 31);
+  const double v2 = __shfl_sync(0xffffffffu, src, (c0 + 2) & 31);
+  const double v3 = __shfl_sync(0xffffffffu, src, (c0 + 3) & 31);
+  const double x3 = v3;
+  const double x2 = fma(-k.l32, x3, v2);
+  const double x1 = fma(-k.l21, x2, fma(-k.l31, x3, v1));
+  const double x0 = fma(-k.l10, x1, fma(-k.l20, x2, fma(-k.l30, x3, v0)));
+  const double xs = (lane & 3) == 0 ? x0 : (lane & 3) == 1 ? x1 : (lane & 3) == 2 ? x2 : x3;
+  if (HI) {
+    const int rr = lane + 32;
+    const double u1 = fma(-k.b0, x0, fma(-k.b1, x1, fma(-k.b2, x2, fma(-k.b3, x3, y1))));
+    y1 = rr < c0 ? u1 : (rr < c0 + 4 ? xs : y1);
+    y0 = fma(-k.a0, x0, fma(-k.a1, x1, fma(-k.a2, x2, fma(-k.a3, x3, y0))));
+  } else {
+    const double u0 = fma(-k.a0, x0, fma(-k.a1, x1, fma(-k.a2, x2, fma(-k.a3, x3, y0))));
+    y0 = lane < c0 ? u0 : (lane < c0 + 4 ? xs : y0);
+  }
+}
+__device__ __forceinline__ void tri64_backward(const double* T, double* y, int lane) {
+  double y0 = y[lane], y1 = y[lane + 32];
+  TriBwd ka, kb;
+  tri64_backward_load(ka, T, 15, lane);
+#pragma unroll 1
+  for (int b = 15; b >= 8; b -= 2) {
+    tri64_backward_load(kb, T, b - 1, lane);
+    tri64_backward_block<true>(ka, b, y0, y1, lane);
+    tri64_backward_load(ka, T, b - 2, lane);
+    tri64_backward_block<true>(kb, b - 1, y0, y1, lane);
+  }
+#pragma unroll 1
+  for (int b = 7; b >= 0; b -= 2) {
+    tri64_backward_load(kb, T, b - 1, lane);
+    tri64_backward_block<false>(ka, b, y0, y1, lane);
+    tri64_backward_load(ka, T, b - 2 >= 0 ? b - 2 : 0, lane);
+    tri64_backward_block<false>(kb, b - 1, y0, y1, lane);
+  }
+  y[lane] = y0;
+  y[lane + 32] = y1;
+}
+
+__device__ void ldlt_solve(const double* K, const double* Dg, int N, double* x, double* sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (N + SB64 - 1) / SB64;
+  const int ntile = nblk * (nblk + 1) / 2, nsteps = 2 * ntile;
   double* sx = sm;
-  double* Ld = sx + nblk * SB64;
-  double* part = Ld + SB64 * SP65;
+  double* ring = sx + nblk * SB64;
+  TileCursor lc, cc;  // load cursor (SOLVE_STAGES - 1 steps ahead) and compute cursor
+  int lk = 0;
+  __syncthreads();  // the previous phase is done with this shared memory; g_svph of the previous solve is visible
+  unsigned ph = g_svph;
+  auto issue = [&]() {  // thread 0: tile of step lk -> its stage
+    if (lk < nsteps) {
+      solve_tile_issue(ring + (lk % SOLVE_STAGES) * TILE_DOUBLES, g_svbar + lk % SOLVE_STAGES, K, lc.r, lc.c);
+      lc.advance(lk, ntile);
+    }
+    ++lk;
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < SOLVE_STAGES - 1; ++k) issue();
+  }
   for (int i = tid; i < nblk * SB64; i += FT) sx[i] = i < N ? x[i] : 0.0;
-  __syncthreads();
-  // forward
-  for (int r = 0; r < nblk; ++r) {
-    const int R0 = r * SB64, nr = min(SB64, N - R0);
-    for (int idx = tid; idx < SB64 * SB64; idx += FT) {
-      const int i = idx >> 6, c = idx & 63;
-      Ld[i * SP65 + c] = (i < nr && c < i) ? K[(size_t)(R0 + i) * ld + R0 + c] : 0.0;
+  const int ti = tid >> 2, tp = tid & 3;  // off-diagonal tiles: 4 lanes per row (forward) / column (backward)
+  for (int k = 0; k < nsteps; ++k) {
+#ifdef IPMZ_FUSED_CLOCKS
+    const long long tk0 = clock64();
+#endif
+    // warp 0 alone polls the stage's mbarrier; the other warps sleep in the hardware barrier (eight warps spinning on
+    // try_wait would take issue slots from the co-resident CTA)
+    if (warp == 0) mbar_wait(g_svbar + k % SOLVE_STAGES, (ph >> (k % SOLVE_STAGES)) & 1u);  // all lanes: they read the tile next
+    ph ^= 1u << (k % SOLVE_STAGES);
+    __syncthreads();  // tile k has landed; step k - 1 is finished, its stage is free
+    if (tid == 0) issue();
+#ifdef IPMZ_FUSED_CLOCKS
+    const long long tk1 = clock64();
+#endif
+    if (k == ntile) {  // between the sweeps: the pivots
+      for (int i = tid; i < N; i += FT) sx[i] = sx[i] / Dg[i];
+      __syncthreads();
     }
-    double sacc[8];
+    const double* T = ring + (k % SOLVE_STAGES) * TILE_DOUBLES;
+    const int r = cc.r, c = cc.c;
+    cc.advance(k, ntile);
+    const int R0 = r * SB64, C0 = c * SB64;
+    if (k < ntile) {
+      if (c < r) {  // y_r -= L(r,c) x_c
+        const double* Tr = T + ti * TP + tp;
+        const double* xc = sx + C0 + tp;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sacc[i] = 0.0;
-    for (int c0 = 0; c0 < R0; c0 += 64) {
-      const double xa = sx[c0 + lane], xb = sx[c0 + 32 + lane];
-      double la[8], lb[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 8 * warp + i;
-        const double* Kr = K + (size_t)(R0 + (row < nr ? row : 0)) * ld + c0 + lane;
-        la[i] = row < nr ? Kr[0] : 0.0;
-        lb[i] = row < nr ? Kr[32] : 0.0;
+        for (int j = 0; j < 16; j += 2) {
+          s0 = fma(Tr[4 * j], xc[4 * j], s0);
+          s1 = fma(Tr[4 * j + 4], xc[4 * j + 4], s1);
+        }
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (tp == 0) sx[R0 + ti] -= s;
+      } else if (warp == 0) {  // unit lower triangular 64 x 64
+        tri64_forward(T, sx + R0, lane);
       }
+    } else {
+      if (c < r) {  // x_c -= L(r,c)^T x_r
+        const double* Tc = T + tp * TP + ti;
+        const double* xr = sx + R0 + tp;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sacc[i] = fma(lb[i], xb, fma(la[i], xa, sacc[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double t = wsum(sacc[i]);
-      if (lane == 0) sx[R0 + 8 * warp + i] -= t;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double y0 = sx[R0 + lane], y1 = sx[R0 + lane + 32];
-#pragma unroll 8
-      for (int c = 0; c < SB64; ++c) {
-        const double yc = __shfl_sync(0xffffffffu, c < 32 ? y0 : y1, c & 31);
-        if (lane > c) y0 -= Ld[lane * SP65 + c] * yc;
-        if (lane + 32 > c) y1 -= Ld[(lane + 32) * SP65 + c] * yc;
+        for (int j = 0; j < 16; j += 2) {
+          s0 = fma(Tc[4 * j * TP], xr[4 * j], s0);
+          s1 = fma(Tc[(4 * j + 4) * TP], xr[4 * j + 4], s1);
+        }
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (tp == 0) sx[C0 + ti] -= s;
+      } else if (warp == 0) {  // unit upper triangular (the transposed tile)
+        tri64_backward(T, sx + R0, lane);
       }
-      sx[R0 + lane] = y0;
-      sx[R0 + lane + 32] = y1;
     }
-    __syncthreads();
+#ifdef IPMZ_FUSED_CLOCKS
+    if (tid == 0) {
+      const long long tk2 = clock64();
+      atomicAdd(&g_fused_clk[9], (unsigned long long)(tk1 - tk0));
+      atomicAdd(&g_fused_clk[c == r ? 10 : 11], (unsigned long long)(tk2 - tk1));
+      atomicAdd(&g_fused_clk[c == r ? 12 : 13], 1ull);
+    }
+#endif
   }
-  for (int i = tid; i < N; i += FT) sx[i] = sx[i] / Dg[i];
   __syncthreads();
-  // backward
-  const int c = tid & 63, grp = tid >> 6;
-  for (int r = nblk - 1; r >= 0; --r) {
-    const int R0 = r * SB64, nr = min(SB64, N - R0);
-    for (int idx = tid; idx < SB64 * SB64; idx += FT) {
-      const int i = idx >> 6, cc = idx & 63;
-      Ld[i * SP65 + cc] = (i < nr && cc < i) ? K[(size_t)(R0 + i) * ld + R0 + cc] : 0.0;
-    }
-    double sacc = 0.0;
-    if (c < nr) {
-      double p8[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) p8[u] = 0.0;
-      int row = R0 + SB64 + grp;
-      for (; row + 28 < N; row += 32) {
-        double lv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) lv[u] = K[(size_t)(row + 4 * u) * ld + R0 + c];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) p8[u] = fma(lv[u], sx[row + 4 * u], p8[u]);
-      }
-      for (; row < N; row += 4) p8[0] = fma(K[(size_t)row * ld + R0 + c], sx[row], p8[0]);
-      sacc = ((p8[0] + p8[1]) + (p8[2] + p8[3])) + ((p8[4] + p8[5]) + (p8[6] + p8[7]));
-    }
-    part[grp * SB64 + c] = sacc;
-    __syncthreads();
-    if (tid < SB64) sx[R0 + tid] -= (part[tid] + part[SB64 + tid]) + (part[2 * SB64 + tid] + part[3 * SB64 + tid]);
-    __syncthreads();
-    if (warp == 0) {
-      double x0 = sx[R0 + lane], x1 = sx[R0 + lane + 32];
-#pragma unroll 8
-      for (int i = SB64 - 1; i >= 0; --i) {
-        const double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
-        if (lane < i) x0 -= Ld[i * SP65 + lane] * xi;
-        if (lane + 32 < i) x1 -= Ld[i * SP65 + lane + 32] * xi;
-      }
-      sx[R0 + lane] = x0;
-      sx[R0 + lane + 32] = x1;
-    }
-    __syncthreads();
-  }
+  if (tid == 0) g_svph = ph;
   for (int i = tid; i < N; i += FT) x[i] = sx[i];
   __syncthreads();
 }
@@ -579,14 +821,14 @@ __device__ void condensed_solve(const View& v, int p, const double* rvec, int ac
   if (s.m > 0) {
     for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, rvec, 0);
     __syncthreads();
-    MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, v.tm + (size_t)p * s.ms, v.tn + (size_t)p * s.ns);
+    MATVEC_T(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, v.tm + (size_t)p * s.ms, v.tn + (size_t)p * s.ns);
     __syncthreads();
   }
   for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, rvec, 1);
   __syncthreads();
   {
     FSUB_BEGIN;
-    ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sol, sm);
+    ldlt_solve(v.K + (size_t)p * v.sK, v.Dg + (size_t)p * v.ldk, v.N, sol, sm);
     FSUB_END(8);
   }
   if (s.m > 0) {
@@ -606,15 +848,15 @@ __device__ void newton_direction(const View& v, int p, int nref, double (*red)[F
   if (!v.normal) {
     for (int i = tid; i < len; i += FT) prepare_sol_body(v, p, i, v.rhs, 0);
     __syncthreads();
-    ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, v.sol + (size_t)p * v.ssol, sm);
+    ldlt_solve(v.K + (size_t)p * v.sK, v.Dg + (size_t)p * v.ldk, v.N, v.sol + (size_t)p * v.ssol, sm);
   } else {
     (void)rhs;
     condensed_solve(v, p, v.rhs, 0, sm);
     double* out = v.out + (size_t)p * (s.ns + s.ms);
     for (int r = 0; r < nref; ++r) {
-      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, out, v.Qd + (size_t)p * s.ns);
+      MATVEC_Q(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, out, v.Qd + (size_t)p * s.ns);
       if (s.m > 0) {
-        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, out + s.ns, v.tn + (size_t)p * s.ns);
+        MATVEC_T(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, out + s.ns, v.tn + (size_t)p * s.ns);
         // first refinement step: out's dx is still the vector the condensed solve just multiplied by M (Mx)
         if (r > 0) MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, out, v.Mx + (size_t)p * s.ms);
       }
@@ -642,7 +884,9 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
   __shared__ int s_p;
   if (threadIdx.x == 0) {
     for (int i = 0; i < MV_NBUF; ++i) mbar_init(g_mvbar + i, 1);
+    for (int i = 0; i < SOLVE_STAGES; ++i) mbar_init(g_svbar + i, 1);
     g_mvph = 0;
+    g_svph = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -676,24 +920,9 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
         __syncthreads();
         continue;
       }
-      // initial point (EnvironmentBuilder.cpp:34-73) and M^T, as ipmz_batch_upload's kernels would have left them
+      // initial point (EnvironmentBuilder.cpp:34-73), as ipmz_batch_upload's kernel would have left it (the fused path
+      // never reads the transposed copy M^T the upload path builds for the grid-per-phase kernels)
       for (int i = tid; i < len; i += FT) initial_point_body(v, p, i);
-      if (s.m > 0) {
-        const double* M = v.M + (size_t)p * v.sM;
-        double* MT = a.MT_w + (size_t)p * v.sMT;
-        const int lane = tid & 31, warp = tid >> 5;
-        double* tile = sm + warp * (32 * 33);
-        const int tr = (s.m + 31) >> 5, tc = (s.n + 31) >> 5;
-        for (int t = warp; t < tr * tc; t += FW) {
-          const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
-          for (int i = 0; i < 32; ++i)
-            tile[i * 33 + lane] = (r0 + i < s.m && c0 + lane < s.n) ? M[(size_t)(r0 + i) * v.ldm + c0 + lane] : 0.0;
-          __syncwarp();
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < s.n && r0 + lane < s.m) MT[(size_t)(c0 + i) * v.ldmt + r0 + lane] = tile[lane * 33 + i];
-          __syncwarp();
-        }
-      }
       __syncthreads();
     }
     if (tid == 0) {  // a fresh solve restarts the counters and keeps the iterate (warm start, as ipmz_solve)
@@ -703,15 +932,15 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
 #ifdef IPMZ_FUSED_DBG_MODES
     if (a.dbg == 1) {
       for (int rep = 0; rep < 30; ++rep) {
-        MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
-        MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
-        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
+        MATVEC_Q(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+        MATVEC_BOTH(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms, V + (size_t)N_NSLOTS * s.ns,
+                    v.MTl + (size_t)p * s.ns);
       }
       __syncthreads();
       continue;
     }
     if (a.dbg >= 2) {
-      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+      MATVEC_Q(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
       MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
       __syncthreads();
       {
@@ -721,8 +950,8 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
       }
       for (int rep = 0; rep < 20; ++rep) {
         assemble_normal(v, p, sm);
-        if (a.dbg >= 3) ldlt_panels(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sm);
-        if (a.dbg >= 4) ldlt_solve(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, v.sol + (size_t)p * v.ssol, sm);
+        if (a.dbg >= 3) ldlt_panels(v.K + (size_t)p * v.sK, v.Dg + (size_t)p * v.ldk, v.N, sm);
+        if (a.dbg >= 4) ldlt_solve(v.K + (size_t)p * v.sK, v.Dg + (size_t)p * v.ldk, v.N, v.sol + (size_t)p * v.ssol, sm);
       }
       __syncthreads();
       continue;
@@ -731,10 +960,10 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
     FPH_DECL;
     for (;;) {
       // ---- Q x, M x, M^T lambda
-      MATVEC(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
+      MATVEC_Q(v.Q + (size_t)p * v.sQ, v.ldq, s.n, s.n, V, v.Qx + (size_t)p * s.ns);
       if (s.m > 0) {
-        MATVEC(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms);
-        MATVEC(v.MT + (size_t)p * v.sMT, v.ldmt, s.n, s.m, V + (size_t)N_NSLOTS * s.ns, v.MTl + (size_t)p * s.ns);
+        MATVEC_BOTH(v.M + (size_t)p * v.sM, v.ldm, s.m, s.n, V, v.Mx + (size_t)p * s.ms, V + (size_t)N_NSLOTS * s.ns,
+                    v.MTl + (size_t)p * s.ns);
       }
       __syncthreads();
       FPH(0);
@@ -755,7 +984,7 @@ __global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
       if (v.normal && s.m > 0) assemble_normal(v, p, sm);
       else assemble_augmented(v, p);
       FPH(2);
-      ldlt_panels(v.K + (size_t)p * v.sK, v.ldk, v.Dg + (size_t)p * v.ldk, v.N, sm);
+      ldlt_panels(v.K + (size_t)p * v.sK, v.Dg + (size_t)p * v.ldk, v.N, sm);
       FPH(3);
       // ---- predictor
       newton_direction<0>(v, p, nref, red, sm);
@@ -797,15 +1026,20 @@ int fused_smem_doubles(const View& v) {
   const int ldlt = rows_cap * PP + 32 + 32 + CBUF + INV_SUB;
   const int syrk = FSTAGES * STAGE_DOUBLES + s.ms + s.ns;
   const int nblk = (v.N + SB64 - 1) / SB64;
-  const int solve = nblk * SB64 + SB64 * SP65 + 4 * SB64;
+  const int solve = nblk * SB64 + SOLVE_STAGES * TILE_DOUBLES;
   int m = ldlt > syrk ? ldlt : syrk;
   if (solve > m) m = solve;
-  if (MV_NBUF * MV_CHUNK > m) m = MV_NBUF * MV_CHUNK;
-  if (FW * 32 * 33 > m) m = FW * 32 * 33;  // one 32 x 33 transpose tile per warp (streamed mode)
+  if (MV_NBUF * MV_CHUNK + 512 > m) m = MV_NBUF * MV_CHUNK + 512;  // staging buffers + the staged vector of A^T v
   return m;
 }
 
 }  // namespace
+
+// doubles of one problem's reduced matrix in the fused path's tile-major layout (the workspace allocates at least this)
+size_t fused_k_doubles(int N) {
+  const int nblk = (N + SB64 - 1) / SB64;
+  return (size_t)(nblk * (nblk + 1) / 2) * TILE_DOUBLES;
+}
 
 // Does the persistent one-CTA-per-problem kernel cover this workspace?  AUGMENTED or NORMAL reduction, LDL^T
 // (no Bunch-Kaufman rows), and a panel that fits the shared memory of one CTA.
@@ -834,7 +1068,6 @@ int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed
   FusedArgs a;
   a.ready = ready;
   a.abort_flag = abort_flag;
-  a.MT_w = const_cast<double*>(v.MT);
   a.v = v;
   a.v.active = nullptr;
   a.count = count;

@@ -139,6 +139,7 @@ void launch_syrk_ldl(cudaStream_t st, int nslots, const int* active, const doubl
 
 // ---- batch_fused.cu: the whole IPM solve of one small QP inside one persistent CTA, one launch per batch ----
 bool fused_batch_applicable(const View& v);  // AUGMENTED / NORMAL, LDL^T rows only, panel fits one CTA's shared memory
+size_t fused_k_doubles(int N);               // per-problem doubles of K in the fused path's tile-major layout
 int fused_batch_init();                      // per-device opt-in shared-memory size; returns cudaError_t
 // every problem 0..count-1 from its current iterate to convergence; refine_fixed < 0 = refinement by each problem's mu
 // ready != nullptr: streamed mode -- the grid is launched before the upload and a CTA waits until *ready > its ticket

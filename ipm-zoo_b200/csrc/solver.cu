@@ -312,6 +312,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.N = v.normal ? s.n : (v.full ? v.fl.N : w->Naug);
   v.ldk = pad4(v.N);
   v.sK = (size_t)v.N * v.ldk;
+  if (batch_handle && v.N <= 512) v.sK = std::max(v.sK, fused_k_doubles(v.N));  // tile-major layout of the fused batch kernel
   v.ldq = s.ns; v.ldm = s.ns; v.ldmt = s.ms;
   v.sQ = (size_t)s.n * s.ns; v.sM = (size_t)s.m * s.ns; v.sMT = (size_t)s.n * s.ms;
   v.sp = (size_t)N_NSLOTS * s.ns + (size_t)N_MSLOTS * s.ms;

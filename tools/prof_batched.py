@@ -29,7 +29,8 @@ if hasattr(z.lib(), "ipmz_debug_fused_clocks") and z.lib().ipmz_debug_fused_cloc
     names = ["matvecs", "residuals", "assembly", "ldlt", "predictor", "mu+rhs", "corrector", "update"]
     tot = float(sum(clk))
     if clk[12]:
-        print("  matvec per chunk (cycles): wait %.0f compute %.0f sync+issue %.0f over %d chunks" % (clk[9] / clk[12], clk[10] / clk[12], clk[11] / clk[12], clk[12]))
+        print("  solve tiles (cycles per step): wait+barrier+issue %.0f; diagonal chain %.0f (x%d); off-diagonal %.0f (x%d)"
+              % (clk[9] / (clk[12] + clk[13]), clk[10] / clk[12], clk[12], clk[11] / max(1, clk[13]), clk[13]))
     tot = float(sum(clk[:8])) or 1.0
     print("phase clocks (both reps): " + ", ".join("%s %.1f%%" % (names[i], 100.0 * clk[i] / tot) for i in range(8)))
-    print("  inside predictor/corrector: " + ", ".join("sub%d %.1f%%" % (i, 100.0 * clk[i] / tot) for i in range(8, 16) if clk[i]))
+    print("  inside predictor/corrector: " + ", ".join("sub%d %.1f%%" % (i, 100.0 * clk[i] / tot) for i in range(8, 9) if clk[i]))
