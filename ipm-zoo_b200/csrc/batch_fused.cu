@@ -464,7 +464,7 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
       const int r = idx >> 4, c = (idx & 15) * 2;
       int bytes = 0;
       if (r < R && c < jb && !(r < jb && c > r)) bytes = (jb - c >= 2) ? 16 : 8;
-      cp_async16(P + r * PP + c, K + kidx(j0 + (bytes ? r : 0), j0 + (bytes ? c : 0)), bytes);
+      cp_async16(P + r * PP + c, K + kidx(j0 + (bytes ? r : 0), j0) + (bytes ? c : 0), bytes);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -480,7 +480,7 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
     // ---- L and the pivots back to global memory
     for (int idx = tid; idx < R * SB; idx += FT) {
       const int r = idx >> 5, c = idx & 31;
-      if (c < jb && (r >= jb || c < r)) K[kidx(j0 + r, j0 + c)] = P[r * PP + c];
+      if (c < jb && (r >= jb || c < r)) K[kidx(j0 + r, j0) + c] = P[r * PP + c];
     }
     if (tid < jb) Dg[j0 + tid] = dsm[tid];
     // ---- trailing update  C -= L_panel diag(d) L_panel^T  on the lower triangle, 16 x 16 tiles per warp
@@ -497,7 +497,12 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
         while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
         ni = t - mi * (mi + 1) / 2;
       };
+      // a 16 x 16 tile of the trailing matrix (t0 is a multiple of 32) lies inside one 64 x 64 storage tile: one tile
+      // base per task, constant per-lane offsets
+      const int lane_off = g * TP + 2 * q;
+      auto tile_ptr = [&](int mi, int ni) -> size_t { return kidx(t0 + mi * 16, t0 + ni * 16) + lane_off; };
       auto load_c = [&](int mi, int ni, double2 (&cv)[2][2]) {
+        const double* base = K + tile_ptr(mi, ni);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -505,7 +510,7 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
             const int row = mi * 16 + i * 8 + g, col = ni * 16 + j * 8 + 2 * q;
             cv[i][j] = make_double2(0.0, 0.0);
             if (row < rem && col <= row) {
-              const double* src = K + kidx(t0 + row, t0 + col);
+              const double* src = base + i * 8 * TP + j * 8;
               if (col + 1 <= row) cv[i][j] = *reinterpret_cast<const double2*>(src);
               else cv[i][j].x = src[0];
             }
@@ -546,13 +551,14 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
             dmma884(acc[1][1], af[k4][1], bf[k4][1]);
           }
         }
+        double* obase = K + tile_ptr(mi, ni);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int row = mi * 16 + i * 8 + g, col = ni * 16 + j * 8 + 2 * q;
             if (row < rem && col <= row) {
-              double* dst = K + kidx(t0 + row, t0 + col);
+              double* dst = obase + i * 8 * TP + j * 8;
               if (col + 1 <= row) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
               else dst[0] = acc[i][j][0];
             }
