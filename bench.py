@@ -609,6 +609,25 @@ def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
                            "note": "condensed assembly n^2 m + LDL^T n^3/3 (FP64 DMMA); input bytes per problem %d"
                                    % ((n * n + m * n + 3 * n + 2 * m) * 8)}}
     out["tflops_device"] = it_sum * out["algorithmic"]["flops_per_problem_iteration"] / t_dev * 1e-12
+    # roofline of the one kernel of the batched path: the contraction flops (assembly + LDL^T) against the live DMMA probe;
+    # DRAM traffic per problem from the committed ncu capture of the same kernel (profiles/r02_traffic.json)
+    try:
+        peak = float(z.fp64_peak_tflops(local)) * world
+    except Exception:
+        peak = None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")))["k_ipm_batch"]
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["problems"]
+    except Exception:
+        traffic = None
+    out["roofline"] = {"bound": "tensor", "kernel": "k_ipm_batch (whole Mehrotra solve of one QP per CTA)",
+                       "achieved": out["tflops_device"], "peak": peak, "unit": "TFLOP/s",
+                       "frac": out["tflops_device"] / peak if peak else None,
+                       "traffic": traffic, "traffic_unit": "DRAM bytes per problem (profiles/r02_traffic.json); algorithmic "
+                       "input bytes per problem %d: Q, M and the factor of the ~300 problems in flight (1.1 MB each) exceed "
+                       "the 126 MB L2 and are re-streamed every phase" % ((n * n + m * n + 3 * n + 2 * m) * 8),
+                       "launches_per_step": 1}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             cpu, gate_its = batched_cpu_baseline()

@@ -63,11 +63,20 @@ enum {
                                  block, which the reference routes to solve_indefinite_() == ASSERT(false)
                                  (Optimizer.cpp:63-75); here it is factorized with Bunch-Kaufman pivoting
                                  (LinearSolvers.cpp:76-318 on the device).  AUGMENTED reduction only. */
-  IPMZ_EQ_REGULARIZATION = 3  /* EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): objective +
+  IPMZ_EQ_REGULARIZATION = 3, /* EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): objective +
                                  1/2 p^T p, rows C x - d + delta p = 0 with delta = ipmz_options.delta_eq.  Eliminating p
                                  leaves the scalar block -delta^2 I on the diagonal, which the reference's evaluator
                                  cannot assemble (Evaluation.cpp:53-60); here the rows are quasi-definite like any other.
                                  p travels in the `t` slot of the packed iterate.  AUGMENTED or NORMAL reduction. */
+  IPMZ_EQ_PENALTY = 4         /* EqualityHandling::PenaltyFunction and PenaltyFunctionWithExtraDual
+                                 (SymbolicOptimization.cpp:173-183): both give the Newton rows  C dx - mu dlambda_C =
+                                 d + mu lambda_C - C x  (get_newton_system), i.e. the scalar block -mu I that depends on the
+                                 barrier parameter and that the reference's evaluator cannot assemble (Evaluation.cpp:53-60).
+                                 mu follows the reference's loop (Optimizer.cpp:138-181): the matrix is assembled with the
+                                 value the previous iteration left in the environment (sigma mu; 1 before the first iteration,
+                                 EnvironmentBuilder.cpp:48), the predictor's residual with mu = 0, the corrector's with the new
+                                 sigma mu.  Only the multiplier exists (no slacks).  AUGMENTED reduction only (condensing -mu I
+                                 onto dx would put C^T C / mu, mu -> 0, into the matrix). */
 };
 
 /* Which reduction of the Newton system is assembled and factorized (north_star). */

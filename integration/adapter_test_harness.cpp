@@ -33,6 +33,8 @@ extern "C" int adapter_solve(int n, int mi, int me, const double* Q, const doubl
     settings.equalities = equalities != 0;
     settings.equality_handling = equalities == 1   ? SymbolicOptimization::EqualityHandling::SlackedSlacks
                                  : equalities == 3 ? SymbolicOptimization::EqualityHandling::Regularization
+                                 : equalities == 4 ? SymbolicOptimization::EqualityHandling::PenaltyFunction
+                                 : equalities == 5 ? SymbolicOptimization::EqualityHandling::PenaltyFunctionWithExtraDual
                                                    : SymbolicOptimization::EqualityHandling::None;  // 2: None
     const SymbolicOptimization::VariableNames names;
     const auto oe = SymbolicOptimization::get_optimization_expressions(names);

@@ -77,11 +77,19 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   hard_eq_ = eq && !has_var(ns, oe_.s_A_eq) && !v && !w;
   const bool reg_probe = eq && has_var(ns, oe_.p_eq);
   ASSERT(!eq || hard_eq_ || reg_probe || (v && w && has_var(ns, oe_.s_A_eq)),
-         "equalities must use EqualityHandling::SlackedSlacks, None or Regularization");
+         "equalities must use EqualityHandling::SlackedSlacks, None, Regularization or PenaltyFunction*");
   // EqualityHandling::Regularization (SymbolicOptimization.cpp:184-192): p_eq is a variable of the system and the
   // multiplier's diagonal block is the scalar -delta^2 I; p travels in the `t` slot of the packed iterate
   reg_eq_ = eq && has_var(ns, oe_.p_eq);
   if (reg_eq_) hard_eq_ = false;
+  // EqualityHandling::PenaltyFunction / PenaltyFunctionWithExtraDual (SymbolicOptimization.cpp:173-183): like None only the
+  // multiplier exists, but its diagonal block in the augmented system is -mu, not the symbolic zero
+  if (hard_eq_) {
+    const auto& av = augmented_system_.variables;
+    for (size_t i = 0; i < av.size(); ++i)
+      if (av.at(i) == oe_.lambda_A_eq && !(augmented_system_.lhs.at(i).at(i) == Expression::zero)) pen_eq_ = true;
+    if (pen_eq_) hard_eq_ = false;
+  }
 
   size_t nq = 0, mi = 0, me = 0;
   const auto Q = flat_matrix(env_, oe_.Q, &nq);
@@ -103,7 +111,8 @@ B200Optimizer::B200Optimizer(Evaluation::Environment& env,
   p.l_x = lx.data(); p.u_x = ux.data();
   p.ineq_bounds = !ineq ? IPMZ_BOUNDS_NONE : (g && h) ? IPMZ_BOUNDS_BOTH : g ? IPMZ_BOUNDS_LOWER : IPMZ_BOUNDS_UPPER;
   p.var_bounds = (y && z) ? IPMZ_BOUNDS_BOTH : y ? IPMZ_BOUNDS_LOWER : z ? IPMZ_BOUNDS_UPPER : IPMZ_BOUNDS_NONE;
-  p.equalities = !eq ? IPMZ_EQ_OFF : reg_eq_ ? IPMZ_EQ_REGULARIZATION : hard_eq_ ? IPMZ_EQ_NONE : IPMZ_EQ_SLACKED_SLACKS;
+  p.equalities = !eq ? IPMZ_EQ_OFF : reg_eq_ ? IPMZ_EQ_REGULARIZATION : pen_eq_ ? IPMZ_EQ_PENALTY : hard_eq_ ? IPMZ_EQ_NONE
+                     : IPMZ_EQ_SLACKED_SLACKS;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = static_cast<int>(reduction);

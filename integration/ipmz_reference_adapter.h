@@ -44,6 +44,7 @@ class B200Optimizer {
   bool converged_ = false;
   bool reg_eq_ = false;   // EqualityHandling::Regularization: p_eq in the system, block -delta^2 I
   bool hard_eq_ = false;  // EqualityHandling::None: lambda_A_eq without s_A_eq -> indefinite KKT, Bunch-Kaufman
+  bool pen_eq_ = false;   // EqualityHandling::PenaltyFunction*: lambda_A_eq alone with the diagonal block -mu
 };
 
 }  // namespace NumericalOptimization

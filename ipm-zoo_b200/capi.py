@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 AUGMENTED, NORMAL, FULL, DUAL_NORMAL = 0, 1, 2, 3
 NONE, LOWER, UPPER, BOTH = 0, 1, 2, 3
-EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE, EQ_REGULARIZATION = 0, 1, 2, 3  # ipmz_problem.equalities (EqualityHandling)
+EQ_OFF, EQ_SLACKED_SLACKS, EQ_NONE, EQ_REGULARIZATION, EQ_PENALTY = 0, 1, 2, 3, 4  # ipmz_problem.equalities (EqualityHandling)
 dp = C.POINTER(C.c_double)
 
 EXPORTED_SYMBOLS = [

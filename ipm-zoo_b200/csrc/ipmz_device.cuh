@@ -37,6 +37,7 @@ struct Shape {
   int ncomp;         // number of complementarity entries (denominator of mu)
   int hard_eq;       // EqualityHandling::None: equality rows carry lambda_C only (no t, v, w) -> indefinite KKT
   int reg_eq;        // EqualityHandling::Regularization: rows C x - d + delta p = 0, p in the SV slot, block -delta^2 I
+  int pen_eq;        // EqualityHandling::PenaltyFunction*: rows C x - d - mu lambda = 0, multiplier only, block -mu I
   double delta_eq;
 };
 

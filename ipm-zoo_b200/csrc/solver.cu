@@ -190,8 +190,9 @@ static void fill_shape(Shape& s, const ipmz_problem* p) {
   s.clamp_x = ineq ? 0 : 1;
   s.hard_eq = (eq && p->equalities == IPMZ_EQ_NONE) ? 1 : 0;
   s.reg_eq = (eq && p->equalities == IPMZ_EQ_REGULARIZATION) ? 1 : 0;
+  s.pen_eq = (eq && p->equalities == IPMZ_EQ_PENALTY) ? 1 : 0;
   s.delta_eq = 1e-4;  // overwritten from the options by create_workspace
-  s.ncomp = (s.ilo + s.iup) * s.mi + ((s.hard_eq || s.reg_eq) ? 0 : 2 * (s.m - s.mi)) + (s.ylo + s.zup) * s.n;
+  s.ncomp = (s.ilo + s.iup) * s.mi + ((s.hard_eq || s.reg_eq || s.pen_eq) ? 0 : 2 * (s.m - s.mi)) + (s.ylo + s.zup) * s.n;
 }
 
 // host [rows x cols] dense (count blocks back to back) -> device pitched rows
@@ -299,7 +300,11 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.s.delta_eq = opt.delta_eq > 0.0 ? opt.delta_eq : 1e-4;
   if (s.reg_eq && opt.reduction == IPMZ_REDUCTION_FULL)
     return fail(IPMZ_ERR_ARG, "EqualityHandling::Regularization is available in the AUGMENTED and NORMAL reductions");
-  if (opt.reduction == IPMZ_REDUCTION_DUAL_NORMAL && (s.m == 0 || s.reg_eq))
+  // -mu I with mu -> 0: condensing it onto dx puts C^T C / mu into the matrix (the classical ill-conditioning of the
+  // penalty method; the iteration stalls at res ~ 1e-4), the quasi-definite LDL^T has no such problem
+  if (s.pen_eq && opt.reduction != IPMZ_REDUCTION_AUGMENTED)
+    return fail(IPMZ_ERR_ARG, "EqualityHandling::PenaltyFunction* (block -mu I) is available in the AUGMENTED reduction only");
+  if (opt.reduction == IPMZ_REDUCTION_DUAL_NORMAL && (s.m == 0 || s.reg_eq || s.pen_eq))
     return fail(IPMZ_ERR_ARG, "the dual-Schur normal equations need constraint rows with slacks (no rows: Hx alone is "
                               "the AUGMENTED reduction; EqualityHandling::Regularization: AUGMENTED or NORMAL)");
   if (s.hard_eq && opt.reduction != IPMZ_REDUCTION_AUGMENTED)
@@ -1075,7 +1080,7 @@ static int check_same_shape(const ipmz_batch_s* h, const ipmz_problem* data) {
   fill_shape(s, data);
   const Shape& t = h->w->v.s;
   if (data->m_ineq != h->mi_host || data->m_eq != h->me_host || s.n != t.n || s.m != t.m || s.mi != t.mi ||
-      s.ylo != t.ylo || s.zup != t.zup || s.ilo != t.ilo || s.iup != t.iup || s.hard_eq != t.hard_eq || s.reg_eq != t.reg_eq)
+      s.ylo != t.ylo || s.zup != t.zup || s.ilo != t.ilo || s.iup != t.iup || s.hard_eq != t.hard_eq || s.reg_eq != t.reg_eq || s.pen_eq != t.pen_eq)
     return fail(IPMZ_ERR_ARG, "problem data does not match the shape / Settings the batch handle was created with");
   return IPMZ_OK;
 }

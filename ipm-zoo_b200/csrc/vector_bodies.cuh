@@ -18,7 +18,7 @@ __device__ __forceinline__ void initial_point_body(const View& v, int p, int i) 
     nslot(V, s, LAMY)[i] = 1.0; nslot(V, s, LAMZ)[i] = 1.0;
     nslot(V, s, YS)[i] = 1.0; nslot(V, s, ZS)[i] = 1.0;
   }
-  if (i < s.m && (s.hard_eq || s.reg_eq) && i >= s.mi) {  // EqualityHandling::None: only the multiplier exists
+  if (i < s.m && (s.hard_eq || s.reg_eq || s.pen_eq) && i >= s.mi) {  // EqualityHandling::None / Penalty*: only the multiplier exists
     mslot(V, s, LAM)[i] = 1.0;
     mslot(V, s, SV)[i] = s.reg_eq ? 1.0 : 0.0;  // Regularization: p = 1 (EnvironmentBuilder.cpp:56)
     mslot(V, s, LAML)[i] = 0.0; mslot(V, s, LAMU)[i] = 0.0;
@@ -140,6 +140,27 @@ __device__ __forceinline__ void residuals_rhs_body(const View& v, int p, int i, 
       rp = mslot(R, s, SV)[i];
     }
     rhs[s.ns + i] = s.delta_eq * rp + -rlam;
+  } else if (i < s.m && s.pen_eq && i >= s.mi) {
+    // EqualityHandling::PenaltyFunction / PenaltyFunctionWithExtraDual (SymbolicOptimization.cpp:173-183; both reach
+    // get_newton_system as the rows C dx - mu dlambda = d + mu lambda - C x): r_lambda = C x - d - mu lambda.
+    // The reference's loop evaluates the matrix with the mu the previous iteration left behind (sigma mu; 1 before the
+    // first iteration, EnvironmentBuilder.cpp:48), the predictor's r_lambda (and `res`) with mu = 0, the corrector's
+    // with the new sigma mu (Optimizer.cpp:138-181: r_lambda holds mu but no e-vector, so it is simply re-evaluated).
+    double rlam;
+    if (MODE == 0) {
+      const Scal& sc = v.sc[p];
+      const double mu_env = sc.iters == 0 ? 1.0 : sc.mu_c;
+      rlam = v.Mx[(size_t)p * s.ms + i] + -v.lo[(size_t)p * s.ms + i];
+      mslot(R, s, LAM)[i] = rlam;
+      acc[2] += rlam * rlam;
+      v.winv[(size_t)p * s.ms + i] = mu_env;
+      v.W[(size_t)p * s.ms + i] = inv_guard(mu_env);
+    } else {
+      // (v.Mx holds M dx by now in the normal reduction: start from the stored C x - d of this iteration)
+      rlam = mslot(R, s, LAM)[i] + -(mu * mslot(V, s, LAM)[i]);
+      mslot(R, s, LAM)[i] = rlam;
+    }
+    rhs[s.ns + i] = -rlam;
   } else if (i < s.m) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     const double lam = mslot(V, s, LAM)[i], sv = mslot(V, s, SV)[i];
@@ -318,7 +339,9 @@ __device__ __forceinline__ void backsub_step_body(const View& v, int p, int i, d
       if (dx > 0.0) amin = fmin(amin, (v.ux[(size_t)p * s.ns + i] - x) / dx);
     }
   }
-  if (i < s.m && s.hard_eq && i >= s.mi) {
+  if (i < s.m && s.pen_eq && i >= s.mi) {
+    mslot(D, s, LAM)[i] = v.normal ? sol[s.ns + i] : sol[s.n + i];  // free multiplier: no ratio test
+  } else if (i < s.m && s.hard_eq && i >= s.mi) {
     mslot(D, s, LAM)[i] = sol[s.n + i];  // the multiplier is free: no ratio test
   } else if (i < s.m && s.reg_eq && i >= s.mi) {
     const double dlam = v.normal ? sol[s.ns + i] : sol[s.n + i];
@@ -373,7 +396,7 @@ __device__ __forceinline__ void mu_affine_body(const View& v, int p, int i, doub
     if (s.ylo) prod(nslot(V, s, YS)[i], nslot(DA, s, YS)[i], nslot(V, s, LAMY)[i], nslot(DA, s, LAMY)[i]);
     if (s.zup) prod(nslot(V, s, ZS)[i], nslot(DA, s, ZS)[i], nslot(V, s, LAMZ)[i], nslot(DA, s, LAMZ)[i]);
   }
-  if (i < s.m && !((s.hard_eq || s.reg_eq) && i >= s.mi)) {
+  if (i < s.m && !((s.hard_eq || s.reg_eq || s.pen_eq) && i >= s.mi)) {
     const int lo = (i < s.mi) ? s.ilo : 1, up = (i < s.mi) ? s.iup : 1;
     if (lo) prod(mslot(V, s, SL)[i], mslot(DA, s, SL)[i], mslot(V, s, LAML)[i], mslot(DA, s, LAML)[i]);
     if (up) prod(mslot(V, s, SU)[i], mslot(DA, s, SU)[i], mslot(V, s, LAMU)[i], mslot(DA, s, LAMU)[i]);

@@ -72,8 +72,10 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   // EqualityHandling::Regularization leaves the scalar block -delta^2 I the reference's evaluator cannot assemble
   // (Evaluation.cpp:53-60); the library treats those rows as quasi-definite rows (p travels in the `t` slot).
   reg_eq_ = settings.equalities && settings.equality_handling == EqualityHandling::Regularization;
-  if (settings.equalities && !hard_eq && !reg_eq_ && settings.equality_handling != EqualityHandling::SlackedSlacks)
-    throw AssertionError("Assertion failed: equalities need EqualityHandling::SlackedSlacks, None or Regularization");
+  const bool pen_eq = settings.equalities && (settings.equality_handling == EqualityHandling::PenaltyFunction ||
+                                              settings.equality_handling == EqualityHandling::PenaltyFunctionWithExtraDual);
+  if (settings.equalities && !hard_eq && !reg_eq_ && !pen_eq && settings.equality_handling != EqualityHandling::SlackedSlacks)
+    throw AssertionError("Assertion failed: equalities need EqualityHandling::SlackedSlacks, None, Regularization or PenaltyFunction*");
   n_ = (int)data.Q.size();
   mi_ = settings.inequalities == Bounds::None ? 0 : (int)data.A_ineq.size();
   me_ = settings.equalities ? (int)data.A_eq.size() : 0;
@@ -89,7 +91,8 @@ Optimizer::Optimizer(Environment& env, const Data& data, const SymbolicOptimizat
   p.l_x = data.l_x.data(); p.u_x = data.u_x.data();
   p.ineq_bounds = mi_ ? bounds_code(settings.inequalities) : IPMZ_BOUNDS_NONE;
   p.var_bounds = bounds_code(settings.variable_bounds);
-  p.equalities = me_ ? (hard_eq ? IPMZ_EQ_NONE : reg_eq_ ? IPMZ_EQ_REGULARIZATION : IPMZ_EQ_SLACKED_SLACKS) : IPMZ_EQ_OFF;
+  p.equalities = me_ ? (hard_eq ? IPMZ_EQ_NONE : reg_eq_ ? IPMZ_EQ_REGULARIZATION : pen_eq ? IPMZ_EQ_PENALTY : IPMZ_EQ_SLACKED_SLACKS)
+                     : IPMZ_EQ_OFF;
   ipmz_options opt;
   ipmz_default_options(&opt);
   opt.reduction = (int)reduction;

@@ -62,6 +62,29 @@ def test_reference_adapter_equality_handling_none():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(SO), reason="adapter test library not prebuilt")
+@pytest.mark.parametrize("handling", [4, 5])
+def test_reference_adapter_equality_handling_penalty(handling):
+    """EqualityHandling::PenaltyFunction (4) / PenaltyFunctionWithExtraDual (5) through the reference's own symbolic
+    layer: the adapter recognises the diagonal block -mu of the multiplier row in get_augmented_system's output and
+    routes it to IPMZ_EQ_PENALTY; the result is the iteration of tests/penalty_model.py."""
+    import penalty_model as pm
+    L = C.CDLL(SO)
+    p = CASES["eq_box_40x20"]()
+    tr = pm.solve(p.Q, p.c, p.C, p.d, p.l_x, p.u_x)
+    x = np.zeros(p.n)
+    it, conv = C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    P = lambda a: a.ctypes.data_as(dp) if a is not None and a.size else None
+    rc = L.adapter_solve(p.n, 0, p.m_eq, P(p.Q), P(p.c), None, None, None, P(p.C), P(p.d), P(p.l_x), P(p.u_x),
+                         0, p.var_bounds, handling, 0, P(x), C.byref(it), C.byref(conv), err, 512)
+    assert rc == 0, err.value.decode()
+    assert conv.value == 1 and it.value == tr["iterations"]
+    assert np.max(np.abs(x - tr["x"])) < 1e-6
+    assert np.max(np.abs(p.C @ x - p.d)) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SO), reason="adapter test library not prebuilt")
 def test_reference_adapter_equality_handling_regularization():
     """EqualityHandling::Regularization through the reference's symbolic layer: p_eq is a variable of the Newton
     system and delta_eq comes from the reference's Environment (EnvironmentBuilder.cpp:48); the reference's own
