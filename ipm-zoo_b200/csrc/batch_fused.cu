@@ -238,8 +238,13 @@ __device__ __noinline__ void cta_matvec_tma(const double* __restrict__ A, int ld
     if (ROWDOT) {
       const double2* a2 = reinterpret_cast<const double2*>(buf + (size_t)(rr < nr ? rr : 0) * lda) + seg;
       double2 av[8];
+      if (exact) {  // uniform branch: no zero-initialisation / predicates on the common path
 #pragma unroll
-      for (int j = 0; j < 8; ++j) av[j] = (exact || seg + S * j < c2) ? a2[S * j] : make_double2(0.0, 0.0);
+        for (int j = 0; j < 8; ++j) av[j] = a2[S * j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = seg + S * j < c2 ? a2[S * j] : make_double2(0.0, 0.0);
+      }
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
@@ -459,12 +464,16 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
     const int jb = min(SB, N - j0);
     const int R = N - j0;                 // rows of the panel (diagonal block included)
     const int R16 = (R + 15) & ~15;
-    // ---- panel -> shared memory (rows beyond R and columns beyond jb as zeros; the diagonal block's upper part too)
-    for (int idx = tid; idx < R16 * (SB / 2); idx += FT) {
-      const int r = idx >> 4, c = (idx & 15) * 2;
-      int bytes = 0;
-      if (r < R && c < jb && !(r < jb && c > r)) bytes = (jb - c >= 2) ? 16 : 8;
-      cp_async16(P + r * PP + c, K + kidx(j0 + (bytes ? r : 0), j0) + (bytes ? c : 0), bytes);
+    // ---- panel -> shared memory (rows beyond R and columns beyond jb as zeros; the diagonal block's upper part too).
+    // A thread keeps its chunk column and walks down the rows 16 at a time: the tile-major row address is one
+    // kidx() per row visited, the diagonal block's triangle test only touches the first two trips.
+    {
+      const int c = (tid & 15) * 2;
+      for (int r = tid >> 4; r < R16; r += FT / 16) {
+        int bytes = 0;
+        if (r < R && c < jb && !(r < jb && c > r)) bytes = (jb - c >= 2) ? 16 : 8;
+        cp_async16(P + r * PP + c, K + kidx(j0 + (bytes ? r : 0), j0) + (bytes ? c : 0), bytes);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -477,10 +486,16 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
       panel_solve32<PP>(P + SB * PP, rem, P, dsm, binv, warp, lane, FW);
       __syncthreads();
     }
-    // ---- L and the pivots back to global memory
-    for (int idx = tid; idx < R * SB; idx += FT) {
+    // ---- L and the pivots back to global memory: the strict lower triangle of the diagonal block element-wise, the
+    // rows below it as 16-byte stores (jb == 32 whenever rows below exist)
+    for (int idx = tid; idx < jb * SB; idx += FT) {
       const int r = idx >> 5, c = idx & 31;
-      if (c < jb && (r >= jb || c < r)) K[kidx(j0 + r, j0) + c] = P[r * PP + c];
+      if (c < r) K[kidx(j0 + r, j0) + c] = P[r * PP + c];
+    }
+    {
+      const int c = (tid & 15) * 2;
+      for (int r = jb + (tid >> 4); r < R; r += FT / 16)
+        *reinterpret_cast<double2*>(K + kidx(j0 + r, j0) + c) = *reinterpret_cast<const double2*>(P + r * PP + c);
     }
     if (tid < jb) Dg[j0 + tid] = dsm[tid];
     // ---- trailing update  C -= L_panel diag(d) L_panel^T  on the lower triangle, 16 x 16 tiles per warp
@@ -491,11 +506,11 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
       const int ntask = tm * (tm + 1) / 2;
       // the C values of a warp's NEXT tile are requested before the DMMAs of the current one (the trailing matrix
       // lives in L2: a tile loaded on demand would expose one L2 round trip per 32 DMMAs)
-      auto tile_of = [&](int t, int& mi, int& ni) {
-        mi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while (mi * (mi + 1) / 2 > t) --mi;
-        while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
-        ni = t - mi * (mi + 1) / 2;
+      // tiles are numbered row by row over the lower triangle; a warp visits t = warp, warp + FW, ...: the (mi, ni)
+      // of the next one follows from the current by walking FW positions (no sqrt decode per tile)
+      auto tile_step = [&](int& mi, int& ni, int by) {
+        ni += by;
+        while (ni > mi) { ni -= mi + 1; ++mi; }
       };
       // a 16 x 16 tile of the trailing matrix (t0 is a multiple of 32) lies inside one 64 x 64 storage tile: one tile
       // base per task, constant per-lane offsets
@@ -518,7 +533,8 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
       };
       double2 cvn[2][2];
       int mi_n = 0, ni_n = 0;
-      if (warp < ntask) { tile_of(warp, mi_n, ni_n); load_c(mi_n, ni_n, cvn); }
+      tile_step(mi_n, ni_n, warp);
+      if (warp < ntask) load_c(mi_n, ni_n, cvn);
       for (int t = warp; t < ntask; t += FW) {
         const int mi = mi_n, ni = ni_n;
         // accumulators start from C and take the products with the sign folded into the B fragment (the reference's own
@@ -529,7 +545,7 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) { acc[i][j][0] = cvn[i][j].x; acc[i][j][1] = cvn[i][j].y; }
-        if (t + FW < ntask) { tile_of(t + FW, mi_n, ni_n); load_c(mi_n, ni_n, cvn); }
+        if (t + FW < ntask) { tile_step(mi_n, ni_n, FW); load_c(mi_n, ni_n, cvn); }
         const int ra = mi * 16 + g, rb = ni * 16 + g;
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh) {
