@@ -451,7 +451,7 @@ def ours(args):
 def bench_configs(z, args, local):
     """cfg1 (n=200, m_eq=100, box; normal-equations reduction), cfg2 (n=2048, m=1024; augmented quasi-definite LDL^T)
     and cfg5 (n=4096 portfolio, eps=1e-6; augmented): whole solve from pinned host buffers through the C ABI
-    (ipmz_create: H2D; ipmz_solve; ipmz_get_iterate: D2H), best of 2 after one warm-up."""
+    (ipmz_create: H2D; ipmz_solve; ipmz_get_iterate: D2H), best of 4 after one warm-up."""
     import problems as P
     cases = [("cfg1", "n=200 m_eq=100 eq(SlackedSlacks)+box, normal equations", lambda: P.eq_box(200, 100, 1), z.NORMAL),
              ("cfg2", "n=2048 m=1024 ineq+box, augmented quasi-definite LDL^T", lambda: P.ineq_box(2048, 1024, 2, kind="shift"),
@@ -472,7 +472,7 @@ def bench_configs(z, args, local):
         pr = z.Problem(pin["Q"], pin["c"], pin.get("A"), pin.get("l_A"), pin.get("u_A"), pin.get("C"), pin.get("d"),
                        pin["l_x"], pin["u_x"], q.ineq_bounds, q.var_bounds, q.equalities)
         best, r = None, None
-        for rep in range(3):
+        for rep in range(5):  # best of 4 after one warm-up (host-side allocation times vary from box to box)
             t0 = time.perf_counter()
             sv = z.Solver(pr, z.Options(reduction=red, device=local))
             r = sv.solve()

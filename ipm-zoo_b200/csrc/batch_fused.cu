@@ -57,7 +57,14 @@ namespace {
 
 constexpr int FT = 256;          // threads per CTA
 constexpr int FW = FT / 32;      // warps
+#ifndef IPMZ_FUSED_CTAS
+#define IPMZ_FUSED_CTAS 2        // resident CTAs per SM the kernel is compiled for (register budget, panel pitch)
+#endif
+#if IPMZ_FUSED_CTAS >= 3
+constexpr int PP = 34;           // three CTAs per SM leave 75 KB each: the 256 x 32 panel fits with pitch 34 (fragment loads 2-way)
+#else
 constexpr int PP = 36;           // panel pitch: 36 mod 16 == 4 -> conflict-free DMMA fragment loads
+#endif
 constexpr int TS = 64;           // assembly tile
 #ifndef IPMZ_FSTAGES
 #define IPMZ_FSTAGES 3
@@ -900,7 +907,7 @@ __device__ void newton_direction(const View& v, int p, int nref, double (*red)[F
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(FT, 2) k_ipm_batch(FusedArgs a) {
+__global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[4][FW];
   __shared__ int s_p;

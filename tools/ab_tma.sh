@@ -7,4 +7,3 @@ for rep in 1 2; do for n in 8192 4096; do
   echo -n "cp.async "; timeout 100 python tools/prof_factor.py $n 5
   echo -n "tma      "; IPMZ_DF_TMA=1 timeout 100 python tools/prof_factor.py $n 5
 done; done
-IPMZ_DF_TMA=1 timeout 300 python tools/dbg_cfg2.py | grep -v trace
