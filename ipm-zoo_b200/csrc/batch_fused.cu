@@ -6,10 +6,11 @@
 // schedule (solver.cu: ~110 launches per iteration, a host synchronisation per iteration to read the stopping test,
 // every matrix pass re-streamed from HBM by a fresh grid) is replaced for systems that fit by:
 //
-//   * a persistent grid (2 CTAs per SM); each CTA pulls problem indices from a ticket counter and runs the complete
-//     solve of that problem -- matvecs, residuals, stopping test, assembly, LDL^T, both Newton solves (with the
-//     normal reduction's iterative refinement), centring, step length and update -- so there is no host round trip
-//     and no wave quantisation: problems that converge early free their CTA for the next ticket;
+//   * a persistent grid (2 CTAs per SM); each CTA takes a problem from a device-side FIFO and runs one complete Mehrotra
+//     iteration of it -- matvecs, residuals, stopping test, assembly, LDL^T, both Newton solves (with the normal
+//     reduction's iterative refinement), centring, step length and update -- then hands the problem back to the queue,
+//     so there is no host round trip and no wave quantisation: the batch advances round robin, problems that converge
+//     leave the queue (see "work distribution" below);
 //   * two co-resident CTAs per SM are always in different phases, so the latency-bound chains of one problem (the
 //     one-warp 32 x 32 LDL^T of a diagonal block, the triangular sweeps, block reductions) overlap the DMMA-bound
 //     phases of the other (condensed assembly M^T W M, trailing updates);
@@ -89,7 +90,8 @@ __device__ __forceinline__ size_t kidx(int row, int col) {
 struct FusedArgs {
   View v;
   int count;
-  int* ticket;
+  int* ticket;       // control words: [0] next fresh problem (ticket), [1] queue head, [2] queue tail, [3] problems finished
+  int* queue;        // FIFO of problems waiting for their next iteration (nullptr: one CTA keeps a problem to the end)
   int refine_fixed;  // >= 0: that many refinement steps per condensed solve; -1: by the problem's mu (solver.cu policy)
   int smem_doubles;
   // streamed solve (ipmz_batch_solve_streamed): the kernel is launched BEFORE the problem data is uploaded; `ready` is a
@@ -907,6 +909,50 @@ __device__ void newton_direction(const View& v, int p, int nref, double (*red)[F
   __syncthreads();
 }
 
+// ---- work distribution ----------------------------------------------------------------------------------------
+// FIFO mode (default): the unit of work is ONE ITERATION of one problem.  A CTA takes a fresh problem if one is resident
+// (ticket < *ready), otherwise the problem at the head of the queue, runs one Mehrotra iteration on it and appends it to
+// the tail unless the stopping test fired.  All of a problem's state between iterations lives in global memory, so any
+// CTA can continue it; the batch then advances round robin and a share of 512 problems keeps all 296 resident CTAs busy
+// to the end (problem-granular tickets: 1.73 waves).  Publication: every thread's stores -> __syncthreads -> thread 0:
+// __threadfence, then the queue slot; acquisition: thread 0 reads the slot, __threadfence (drops stale L1 lines of a
+// problem this SM saw an iteration ago), __syncthreads.
+__device__ __forceinline__ int vload(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void vstore(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// thread 0 only.  Returns the problem (fresh = 1: first touch), -1 when every problem is finished, -2 on the watchdog.
+__device__ __noinline__ int acquire_work(const FusedArgs& a, int& fresh) {
+  int* ctl = a.ticket;
+  const long long t0 = clock64();
+  for (;;) {
+    const int n = vload(ctl + 0);
+    int avail = a.count;
+    if (a.ready) { avail = *a.ready; if (avail > a.count) avail = a.count; }
+    if (n < avail) {
+      if (atomicCAS(ctl + 0, n, n + 1) == n) { fresh = 1; return n; }
+      continue;
+    }
+    const int h = vload(ctl + 1), t = vload(ctl + 2);
+    if (h < t) {
+      if (atomicCAS(ctl + 1, h, h + 1) == h) {  // slot h is ours; its writer bumped the tail first, the value follows
+        int p;
+        while ((p = vload(a.queue + h)) < 0) {}
+        fresh = 0;
+        return p;
+      }
+      continue;
+    }
+    if (vload(ctl + 3) >= a.count) return -1;
+    __nanosleep(300);
+    if (clock64() - t0 > (8ll << 30)) return -2;  // ~4 s without work: an upload that never arrived
+  }
+}
+
 __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ double red[4][FW];
@@ -923,38 +969,57 @@ __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) 
   const Shape& s = v.s;
   const int tid = threadIdx.x;
   const int len = max(s.n, s.m);
+  const bool fifo = a.queue != nullptr;
+  __shared__ int s_fresh;
   for (;;) {
-    if (tid == 0) s_p = atomicAdd(a.ticket, 1);
+    if (tid == 0) {
+      int fr = 1, q;
+      if (fifo) {
+        q = acquire_work(a, fr);
+        __threadfence();
+      } else {
+        q = atomicAdd(a.ticket, 1);
+        if (q >= a.count) q = -1;
+      }
+      s_p = q;
+      s_fresh = fr;
+    }
     __syncthreads();
     const int p = s_p;
+    const int fresh = s_fresh;
     __syncthreads();
-    if (p >= a.count) break;
+    if (p < 0) {
+      if (p == -2 && tid == 0 && a.abort_flag) atomicExch(a.abort_flag, 1);
+      break;
+    }
     Scal& sc = v.sc[p];
-    if (a.ready) {
-      __shared__ int s_ok;
-      if (tid == 0) {
-        const long long t0 = clock64();
-        int ok = 1;
-        while (*a.ready <= p) {
-          __nanosleep(2000);
-          if (clock64() - t0 > (8ll << 30)) { ok = 0; break; }  // ~4 s: the upload never arrived
+    if (fresh && a.ready) {
+      if (!fifo) {  // problem-granular tickets: wait for this problem's data
+        __shared__ int s_ok;
+        if (tid == 0) {
+          const long long t0 = clock64();
+          int ok = 1;
+          while (*a.ready <= p) {
+            __nanosleep(2000);
+            if (clock64() - t0 > (8ll << 30)) { ok = 0; break; }  // ~4 s: the upload never arrived
+          }
+          if (!ok) atomicExch(a.abort_flag, 1);
+          s_ok = ok;
+          __threadfence();
         }
-        if (!ok) atomicExch(a.abort_flag, 1);
-        s_ok = ok;
-        __threadfence();
-      }
-      __syncthreads();
-      if (!s_ok) {
-        if (tid == 0) { sc.iters = 0; sc.done = 3; }
         __syncthreads();
-        continue;
+        if (!s_ok) {
+          if (tid == 0) { sc.iters = 0; sc.done = 3; }
+          __syncthreads();
+          continue;
+        }
       }
       // initial point (EnvironmentBuilder.cpp:34-73), as ipmz_batch_upload's kernel would have left it (the fused path
       // never reads the transposed copy M^T the upload path builds for the grid-per-phase kernels)
       for (int i = tid; i < len; i += FT) initial_point_body(v, p, i);
       __syncthreads();
     }
-    if (tid == 0) {  // a fresh solve restarts the counters and keeps the iterate (warm start, as ipmz_solve)
+    if (fresh && tid == 0) {  // a fresh solve restarts the counters and keeps the iterate (warm start, as ipmz_solve)
       sc.iters = 0; sc.done = 0; sc.mu_c = 0.0; sc.alpha = 0.0; sc.alpha_aff = 0.0; sc.sigma = 0.0;
     }
     double* V = v.V + (size_t)p * v.sp;
@@ -1044,8 +1109,14 @@ __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) 
         if (tid == 0) sc.iters += 1;
       }
       FPH(7);
+      if (fifo) break;  // one iteration per acquisition: the problem goes back to the queue
     }
     __syncthreads();
+    if (fifo && tid == 0) {
+      __threadfence();  // the iteration's stores (all threads, ordered by the barrier above) before the hand-over
+      if (sc.done != 0) atomicAdd(a.ticket + 3, 1);
+      else vstore(a.queue + atomicAdd(a.ticket + 2, 1), p);
+    }
   }
 }
 
@@ -1093,7 +1164,7 @@ int fused_batch_init() {
 // One launch: every problem of the batch from its current iterate to convergence.  `ticket` is a device int the
 // launcher resets on the stream.  Returns a cudaError_t.
 int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket, const int* ready,
-                     int* abort_flag) {
+                     int* abort_flag, int queue_cap) {
   FusedArgs a;
   a.ready = ready;
   a.abort_flag = abort_flag;
@@ -1105,8 +1176,17 @@ int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed
   a.smem_doubles = fused_smem_doubles(v);
   a.dbg = getenv("IPMZ_FUSED_DBG") ? atoi(getenv("IPMZ_FUSED_DBG")) : 0;
   const size_t smem = (size_t)a.smem_doubles * sizeof(double);
-  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int), st);
+  // `ticket`: FUSED_CTL_WORDS control words, then queue_cap queue slots (>= count * (max_iter + 1): every unfinished
+  // iteration of every problem is appended once).  IPMZ_FUSED_QUEUE=0 / debug modes: problem-granular tickets.
+  static const int use_queue = getenv("IPMZ_FUSED_QUEUE") ? atoi(getenv("IPMZ_FUSED_QUEUE")) : 1;
+  const bool fifo = use_queue && a.dbg == 0 && queue_cap >= count * (v.max_iter + 1);
+  a.queue = fifo ? ticket + FUSED_CTL_WORDS : nullptr;
+  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int) * FUSED_CTL_WORDS, st);
   if (e != cudaSuccess) return (int)e;
+  if (fifo) {
+    e = cudaMemsetAsync(a.queue, 0xFF, sizeof(int) * (size_t)count * (v.max_iter + 1), st);  // -1: slot not written yet
+    if (e != cudaSuccess) return (int)e;
+  }
   int dev = 0, nsm = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
