@@ -1148,7 +1148,10 @@ int ipmz_batch_solve_streamed(ipmz_batch_handle h, const ipmz_problem* data, int
   CUDA_TRY(cudaMemsetAsync(w.abort_dev, 0, sizeof(int), w.st));
   CUDA_TRY(cudaEventRecord(w.ev_arm, w.st));
   CUDA_TRY(cudaEventRecord(w.ev0, w.st));
-  const int e = launch_ipm_batch(w.st, v, count, w.refine_auto ? -1 : w.refine, w.fused_ticket, w.ready_dev, w.abort_dev, w.fused_queue_cap);
+  const int e = launch_ipm_batch(w.st, v, count, w.refine_auto ? -1 : w.refine, w.fused_ticket, w.ready_dev, w.abort_dev,
+                                 /* problem-granular tickets: with the upload as the pace-maker a problem should finish as soon as
+                                    it can (round robin would queue the last arrivals behind every open problem: measured
+                                    23.5 vs 22.2 ms end to end on 4 GPUs) */ 0);
   if (e != 0) return fail(IPMZ_ERR_CUDA, std::string("launch_ipm_batch: ") + cudaGetErrorString((cudaError_t)e));
   CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal) * count, cudaMemcpyDeviceToHost, w.st));
   CUDA_TRY(cudaEventRecord(w.ev1, w.st));

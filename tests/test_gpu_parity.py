@@ -320,6 +320,41 @@ def test_batch_streamed_solve_matches_upload_then_solve(z, reduction):
     bs.close()
 
 
+def test_batch_iteration_queue_is_bitwise_the_problem_granular_schedule(z, tmp_path):
+    """k_ipm_batch's default work distribution hands a problem from CTA to CTA between iterations (device FIFO, hand-over
+    by __threadfence + queue slot).  A problem's arithmetic does not depend on who runs it: 700 problems (more than twice
+    the resident CTAs, so every problem migrates between SMs) must give bitwise the iterates of the schedule that keeps
+    a problem on one CTA (IPMZ_FUSED_QUEUE=0, read once per process: run in a child), twice in a row."""
+    import subprocess
+    import sys
+    count, n, m = 700, 40, 16
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import ipm_zoo_b200 as z, problems as P\n"
+        "count, n, m = %d, %d, %d\n"
+        "probs = [P.ineq_box(n, m, 7000 + i, kind='shift') for i in range(count)]\n"
+        "st = lambda key: np.stack([getattr(q, key) for q in probs])\n"
+        "bp = z.Problem(st('Q'), st('c'), st('A'), st('l_A'), st('u_A'), None, None, st('l_x'), st('u_x'))\n"
+        "bs = z.BatchSolver(bp, count, z.Options(reduction=z.NORMAL))\n"
+        "out = []\n"
+        "for rep in range(2):\n"
+        "    bs.upload(); res, ms = bs.solve(); out.append(bs.x().copy())\n"
+        "    assert all(r.converged for r in res)\n"
+        "assert np.array_equal(out[0], out[1])\n"
+        "np.save(sys.argv[1], out[0]); np.save(sys.argv[2], np.array([r.iterations for r in res]))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), count, n, m)
+    outs = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, IPMZ_FUSED_QUEUE=mode)
+        fx, fi = str(tmp_path / ("x%s.npy" % mode)), str(tmp_path / ("i%s.npy" % mode))
+        r = subprocess.run([sys.executable, "-c", code, fx, fi], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[mode] = (np.load(fx), np.load(fi))
+    assert np.array_equal(outs["1"][1], outs["0"][1]), "iteration counts"
+    assert np.array_equal(outs["1"][0], outs["0"][0]), "iterates differ between the two work distributions"
+
+
 def test_batch_upload_rejects_a_different_shape(z):
     count, n, m = 4, 24, 8
     probs = [P.ineq_box(n, m, 50 + i) for i in range(count)]
