@@ -926,13 +926,13 @@ __device__ __forceinline__ void vstore(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 // thread 0 only.  Returns the problem (fresh = 1: first touch), -1 when every problem is finished, -2 on the watchdog.
-__device__ __noinline__ int acquire_work(const FusedArgs& a, int& fresh) {
-  int* ctl = a.ticket;
+// (scalar arguments: passing the kernel's argument struct by reference would move the whole View into local memory)
+__device__ __noinline__ int acquire_work(int* ctl, const int* queue, int count, const volatile int* ready, int& fresh) {
   const long long t0 = clock64();
   for (;;) {
     const int n = vload(ctl + 0);
-    int avail = a.count;
-    if (a.ready) { avail = *a.ready; if (avail > a.count) avail = a.count; }
+    int avail = count;
+    if (ready) { avail = *ready; if (avail > count) avail = count; }
     if (n < avail) {
       if (atomicCAS(ctl + 0, n, n + 1) == n) { fresh = 1; return n; }
       continue;
@@ -941,13 +941,13 @@ __device__ __noinline__ int acquire_work(const FusedArgs& a, int& fresh) {
     if (h < t) {
       if (atomicCAS(ctl + 1, h, h + 1) == h) {  // slot h is ours; its writer bumped the tail first, the value follows
         int p;
-        while ((p = vload(a.queue + h)) < 0) {}
+        while ((p = vload(queue + h)) < 0) {}
         fresh = 0;
         return p;
       }
       continue;
     }
-    if (vload(ctl + 3) >= a.count) return -1;
+    if (vload(ctl + 3) >= count) return -1;
     __nanosleep(300);
     if (clock64() - t0 > (8ll << 30)) return -2;  // ~4 s without work: an upload that never arrived
   }
@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) 
     if (tid == 0) {
       int fr = 1, q;
       if (fifo) {
-        q = acquire_work(a, fr);
+        q = acquire_work(a.ticket, a.queue, a.count, a.ready, fr);
         __threadfence();
       } else {
         q = atomicAdd(a.ticket, 1);

@@ -53,6 +53,12 @@ static int ensure_device(int device) {
   if (device < 64 && !g_factor_init_done[device]) {
     const int rc = factor_init();
     if (rc != 0) return fail(IPMZ_ERR_CUDA, std::string("factor_init: ") + cudaGetErrorString((cudaError_t)rc));
+    // freed handle buffers stay in the device's default pool (up to 16 GB) for the next handle
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = 16ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g_factor_init_done[device] = true;
   }
   return IPMZ_OK;
@@ -146,7 +152,14 @@ struct Workspace {
     lookahead_destroy(&la);
     dataflow_plan_destroy(df);
     dataflow_assembly_plan_destroy(asmp);
-    for (void* p : allocs) cudaFree(p);
+    if (pooled && st) {
+      cudaStreamSynchronize(st);
+      if (cps) cudaStreamSynchronize(cps);
+      for (void* p : allocs) cudaFreeAsync(p, st);  // back to the device's pool: the next handle of this shape reuses it
+      cudaStreamSynchronize(st);
+    } else {
+      for (void* p : allocs) cudaFree(p);
+    }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev_arm) cudaEventDestroy(ev_arm);
@@ -154,8 +167,22 @@ struct Workspace {
     if (cps) cudaStreamDestroy(cps);
     if (st) cudaStreamDestroy(st);
   }
+  // Device buffers of a handle can come from the device's default memory pool, stream-ordered on the handle's stream
+  // (cudaMallocAsync; release threshold raised in ensure_device): creating a handle of a shape that was used before
+  // costs no cudaMalloc.  Opt-in (IPMZ_POOL_ALLOC=1); default: plain cudaMalloc.
+  bool pooled = false;
   template <class T>
   int alloc(T** p, size_t n) {
+    if (pooled && st) {
+      *p = nullptr;
+      if (n == 0) n = 1;
+      cudaError_t e = cudaMallocAsync((void**)p, n * sizeof(T), st);
+      if (e != cudaSuccess) return fail(IPMZ_ERR_ALLOC, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+      allocs.push_back(*p);
+      e = cudaMemsetAsync(*p, 0, n * sizeof(T), st);
+      if (e != cudaSuccess) return fail(IPMZ_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+      return IPMZ_OK;
+    }
     const int rc = dalloc(p, n);
     if (rc == IPMZ_OK) allocs.push_back(*p);
     return rc;
@@ -331,6 +358,10 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   v.maxblk = (len + 255) / 256;
 
   CUDA_TRY(cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("IPMZ_POOL_ALLOC");  // opt-in: measured create 22-27 ms either way at cfg3 size (the 806 MB
+    w->pooled = e && atoi(e) != 0;               // upload dominates) and the pool's first allocation costs 650 ms
+  }
   if (count == 1) {
     const int le = lookahead_create(&w->la);
     if (le != 0) return fail(IPMZ_ERR_CUDA, std::string("lookahead_create: ") + cudaGetErrorString((cudaError_t)le));
