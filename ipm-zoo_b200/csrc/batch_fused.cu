@@ -240,7 +240,7 @@ __device__ __noinline__ void cta_matvec_tma(const double* __restrict__ A, int ld
   const bool col_a = tid < cols, col_b = tid + FT < cols;
   for (int c = 0; c < nch; ++c) {
     const int bi = c % MV_NBUF;
-    mbar_wait(bar + bi, (ph >> bi) & 1u);
+    mbar_wait(bar + bi, (ph >> bi) & 1u);  // (one polling warp + a barrier instead: no gain, 68.5 vs 68.1 ms)
     ph ^= 1u << bi;
     const int r0 = c * R, nr = min(R, rows - r0);
     const double* buf = sm + bi * MV_CHUNK;
