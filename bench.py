@@ -661,7 +661,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batch-reduction", default="normal", choices=["normal", "augmented"])
-    ap.add_argument("--batch-chunks", type=int, default=16, help="upload groups of the streamed end-to-end batch solve")
+    ap.add_argument("--batch-chunks", type=int, default=64, help="upload groups of the streamed end-to-end batch solve")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg2 / cfg5 end-to-end solves")
     ap.add_argument("--quick", action="store_true", help="small sizes (debug only; not a valid bench line)")
     args = ap.parse_args()

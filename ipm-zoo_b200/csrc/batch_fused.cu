@@ -30,6 +30,7 @@
 //   solves             forward / pivots / backward with x in shared memory, 64-row blocks
 //   back-substitution  eliminated Delta's, ratio test, centring parameter, corrector right-hand side, update
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdlib.h>
 
 #include "ipmz_device.cuh"
@@ -90,8 +91,8 @@ __device__ __forceinline__ size_t kidx(int row, int col) {
 struct FusedArgs {
   View v;
   int count;
-  int* ticket;       // control words: [0] next fresh problem (ticket), [1] queue head, [2] queue tail, [3] problems finished
-  int* queue;        // FIFO of problems waiting for their next iteration (nullptr: one CTA keeps a problem to the end)
+  int* ticket;       // control words (see "work distribution"): [0] next fresh problem (ticket), [3] finished, bucket heads / tails
+  int* queue;        // slots of the per-iteration-count buckets (nullptr: one CTA keeps a problem to the end)
   int refine_fixed;  // >= 0: that many refinement steps per condensed solve; -1: by the problem's mu (solver.cu policy)
   int smem_doubles;
   // streamed solve (ipmz_batch_solve_streamed): the kernel is launched BEFORE the problem data is uploaded; `ready` is a
@@ -910,13 +911,18 @@ __device__ void newton_direction(const View& v, int p, int nref, double (*red)[F
 }
 
 // ---- work distribution ----------------------------------------------------------------------------------------
-// FIFO mode (default): the unit of work is ONE ITERATION of one problem.  A CTA takes a fresh problem if one is resident
-// (ticket < *ready), otherwise the problem at the head of the queue, runs one Mehrotra iteration on it and appends it to
-// the tail unless the stopping test fired.  All of a problem's state between iterations lives in global memory, so any
-// CTA can continue it; the batch then advances round robin and a share of 512 problems keeps all 296 resident CTAs busy
-// to the end (problem-granular tickets: 1.73 waves).  Publication: every thread's stores -> __syncthreads -> thread 0:
-// __threadfence, then the queue slot; acquisition: thread 0 reads the slot, __threadfence (drops stale L1 lines of a
-// problem this SM saw an iteration ago), __syncthreads.
+// Queue mode (default): the unit of work is ONE ITERATION of one problem.  All of a problem's state between iterations
+// lives in global memory, so any CTA can continue it.  A CTA takes a fresh problem if one is resident (ticket < *ready),
+// otherwise the waiting problem with the FEWEST iterations done (one FIFO bucket per iteration count, lowest non-empty
+// bucket first), runs one Mehrotra iteration on it and appends it to the next bucket unless the stopping test fired.
+// Least-iterations-first is critical-path-first for chains of similar length: the batch advances as one front, a share
+// of 512 problems keeps all 296 resident CTAs busy to the end (problem-granular tickets: 1.73 waves), and in a streamed
+// solve late arrivals catch up with the front instead of queueing behind it, so everything finishes together shortly
+// after the last upload chunk.  Publication: every thread's stores -> __syncthreads -> thread 0: __threadfence, then the
+// queue slot; acquisition: thread 0 reads the slot, __threadfence (drops stale L1 lines of a problem this SM saw an
+// iteration ago), __syncthreads.
+// Control words: [0] next fresh problem, [3] problems finished, [4] highest bucket used, [8 + 2 b] head and
+// [8 + 2 b + 1] tail of bucket b (b = iterations done, 1 .. max_iter); slots of bucket b at queue + (b - 1) * count.
 __device__ __forceinline__ int vload(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -937,20 +943,34 @@ __device__ __noinline__ int acquire_work(int* ctl, const int* queue, int count, 
       if (atomicCAS(ctl + 0, n, n + 1) == n) { fresh = 1; return n; }
       continue;
     }
-    const int h = vload(ctl + 1), t = vload(ctl + 2);
-    if (h < t) {
-      if (atomicCAS(ctl + 1, h, h + 1) == h) {  // slot h is ours; its writer bumped the tail first, the value follows
-        int p;
-        while ((p = vload(queue + h)) < 0) {}
-        fresh = 0;
-        return p;
+    const int maxb = vload(ctl + 4);
+    bool lost = false;
+    for (int b = 1; b <= maxb; ++b) {
+      int* hb = ctl + 8 + 2 * b;
+      const int h = vload(hb), t = vload(hb + 1);
+      if (h < t) {
+        if (atomicCAS(hb, h, h + 1) == h) {  // slot h is ours; its writer bumped the tail first, the value follows
+          const int* slot = queue + (size_t)(b - 1) * count + h;
+          int p;
+          while ((p = vload(slot)) < 0) {}
+          fresh = 0;
+          return p;
+        }
+        lost = true;  // another CTA took it: look again from the lowest bucket
+        break;
       }
-      continue;
     }
+    if (lost) continue;
     if (vload(ctl + 3) >= count) return -1;
-    __nanosleep(300);
+    __nanosleep(500);
     if (clock64() - t0 > (8ll << 30)) return -2;  // ~4 s without work: an upload that never arrived
   }
+}
+// thread 0 only, after __syncthreads + __threadfence: problem p has `iters` iterations done and needs another one
+__device__ __forceinline__ void release_work(int* ctl, int* queue, int count, int p, int iters) {
+  const int t = atomicAdd(ctl + 8 + 2 * iters + 1, 1);
+  vstore(queue + (size_t)(iters - 1) * count + t, p);
+  atomicMax(ctl + 4, iters);
 }
 
 __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) {
@@ -1115,7 +1135,7 @@ __global__ void __launch_bounds__(FT, IPMZ_FUSED_CTAS) k_ipm_batch(FusedArgs a) 
     if (fifo && tid == 0) {
       __threadfence();  // the iteration's stores (all threads, ordered by the barrier above) before the hand-over
       if (sc.done != 0) atomicAdd(a.ticket + 3, 1);
-      else vstore(a.queue + atomicAdd(a.ticket + 2, 1), p);
+      else release_work(a.ticket, a.queue, a.count, p, sc.iters);
     }
   }
 }
@@ -1163,8 +1183,13 @@ int fused_batch_init() {
 
 // One launch: every problem of the batch from its current iterate to convergence.  `ticket` is a device int the
 // launcher resets on the stream.  Returns a cudaError_t.
+int fused_ctl_words(int max_iter) { return 8 + 2 * (std::max(1, max_iter) + 1); }
+size_t fused_work_words(int count, int max_iter) {
+  return (size_t)fused_ctl_words(max_iter) + (size_t)count * std::max(1, max_iter);
+}
+
 int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket, const int* ready,
-                     int* abort_flag, int queue_cap) {
+                     int* abort_flag, size_t work_words) {
   FusedArgs a;
   a.ready = ready;
   a.abort_flag = abort_flag;
@@ -1176,15 +1201,16 @@ int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed
   a.smem_doubles = fused_smem_doubles(v);
   a.dbg = getenv("IPMZ_FUSED_DBG") ? atoi(getenv("IPMZ_FUSED_DBG")) : 0;
   const size_t smem = (size_t)a.smem_doubles * sizeof(double);
-  // `ticket`: FUSED_CTL_WORDS control words, then queue_cap queue slots (>= count * (max_iter + 1): every unfinished
-  // iteration of every problem is appended once).  IPMZ_FUSED_QUEUE=0 / debug modes: problem-granular tickets.
+  // `ticket`: control words, then the bucket slots (fused_work_words).  IPMZ_FUSED_QUEUE=0 / debug modes / a buffer
+  // that is too small: problem-granular tickets.
   static const int use_queue = getenv("IPMZ_FUSED_QUEUE") ? atoi(getenv("IPMZ_FUSED_QUEUE")) : 1;
-  const bool fifo = use_queue && a.dbg == 0 && queue_cap >= count * (v.max_iter + 1);
-  a.queue = fifo ? ticket + FUSED_CTL_WORDS : nullptr;
-  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int) * FUSED_CTL_WORDS, st);
+  const int ctlw = fused_ctl_words(v.max_iter);
+  const bool fifo = use_queue && a.dbg == 0 && work_words >= fused_work_words(count, v.max_iter);
+  a.queue = fifo ? ticket + ctlw : nullptr;
+  cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(int) * (fifo ? ctlw : 8), st);
   if (e != cudaSuccess) return (int)e;
   if (fifo) {
-    e = cudaMemsetAsync(a.queue, 0xFF, sizeof(int) * (size_t)count * (v.max_iter + 1), st);  // -1: slot not written yet
+    e = cudaMemsetAsync(a.queue, 0xFF, sizeof(int) * (size_t)count * std::max(1, v.max_iter), st);  // -1: slot not written yet
     if (e != cudaSuccess) return (int)e;
   }
   int dev = 0, nsm = 148, per_sm = 1;

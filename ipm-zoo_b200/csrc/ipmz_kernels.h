@@ -143,10 +143,12 @@ size_t fused_k_doubles(int N);               // per-problem doubles of K in the 
 int fused_batch_init();                      // per-device opt-in shared-memory size; returns cudaError_t
 // every problem 0..count-1 from its current iterate to convergence; refine_fixed < 0 = refinement by each problem's mu
 // ready != nullptr: streamed mode -- the grid is launched before the upload and a CTA waits until *ready > its ticket
-// ticket: FUSED_CTL_WORDS control words followed by queue_cap slots of the iteration queue (0: problem-granular tickets)
-constexpr int FUSED_CTL_WORDS = 8;
+// ticket: work_words ints = control words + bucket slots of the iteration queue (fused_work_words; fewer: problem-granular
+// tickets, 8 ints are enough)
+int fused_ctl_words(int max_iter);
+size_t fused_work_words(int count, int max_iter);
 int launch_ipm_batch(cudaStream_t st, const View& v, int count, int refine_fixed, int* ticket,
-                     const int* ready = nullptr, int* abort_flag = nullptr, int queue_cap = 0);
+                     const int* ready = nullptr, int* abort_flag = nullptr, size_t work_words = 0);
 int fused_read_clocks(unsigned long long* out16);  // debug builds (-DIPMZ_FUSED_CLOCKS)
 
 // dst[m x ldd](lower) = -src block (lower), the Schur complement left by a partial elimination, as its own matrix

@@ -123,7 +123,7 @@ struct Workspace {
   int Naug = 0;
   bool fused = false;         // batch handles: the persistent one-CTA-per-problem kernel (batch_fused.cu)
   int* fused_ticket = nullptr;  // control words + iteration queue of the fused batch kernel
-  int fused_queue_cap = 0;
+  size_t fused_queue_cap = 0;
   // streamed solve: copy stream, the device word it overwrites with the number of resident problems, abort flag
   cudaStream_t cps = nullptr;
   cudaEvent_t ev_arm = nullptr;
@@ -401,8 +401,8 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (s.hard_eq) ALLOC(w->ipiv, C * v.ldk);
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
-  w->fused_queue_cap = batch_handle ? count * (std::max(1, opt.max_iter) + 1) : 0;
-  ALLOC(w->fused_ticket, (size_t)FUSED_CTL_WORDS + w->fused_queue_cap);
+  w->fused_queue_cap = batch_handle ? fused_work_words(count, opt.max_iter) : 0;
+  ALLOC(w->fused_ticket, std::max<size_t>(8, w->fused_queue_cap));
   ALLOC(w->ready_dev, 1); ALLOC(w->abort_dev, 1);
   if (count == 1) ALLOC(w->Rlast, v.sp);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
@@ -1180,9 +1180,7 @@ int ipmz_batch_solve_streamed(ipmz_batch_handle h, const ipmz_problem* data, int
   CUDA_TRY(cudaEventRecord(w.ev_arm, w.st));
   CUDA_TRY(cudaEventRecord(w.ev0, w.st));
   const int e = launch_ipm_batch(w.st, v, count, w.refine_auto ? -1 : w.refine, w.fused_ticket, w.ready_dev, w.abort_dev,
-                                 /* problem-granular tickets: with the upload as the pace-maker a problem should finish as soon as
-                                    it can (round robin would queue the last arrivals behind every open problem: measured
-                                    23.5 vs 22.2 ms end to end on 4 GPUs) */ 0);
+                                 w.fused_queue_cap);
   if (e != 0) return fail(IPMZ_ERR_CUDA, std::string("launch_ipm_batch: ") + cudaGetErrorString((cudaError_t)e));
   CUDA_TRY(cudaMemcpyAsync(w.sc_host.data(), v.sc, sizeof(Scal) * count, cudaMemcpyDeviceToHost, w.st));
   CUDA_TRY(cudaEventRecord(w.ev1, w.st));
