@@ -238,6 +238,33 @@ def test_batch_matches_oracle_per_problem(z, reduction):
     bs.close()
 
 
+@pytest.mark.parametrize("n,m", [(37, 15), (1, 1), (65, 0), (130, 61), (257, 127), (300, 211)])
+@pytest.mark.parametrize("reduction", [0, 1])
+def test_batch_ragged_shapes_match_oracle(z, n, m, reduction):
+    """Shapes that are not multiples of the fused batch kernel's 64 x 64 factor tiles, 32-wide panels, 16-row assembly
+    slices or 4-row matvec groups (odd N, N = 1, no constraint rows, N just above a tile / panel edge, N = 511 in the
+    AUGMENTED reduction = the largest the kernel takes), fewer problems than resident CTAs."""
+    count = 5
+    if m > 0:
+        probs = [P.ineq_box(n, m, 3000 + 7 * n + i, kind="shift") for i in range(count)]
+        st = lambda key: np.stack([getattr(q, key) for q in probs])
+        bp = z.Problem(st("Q"), st("c"), st("A"), st("l_A"), st("u_A"), None, None, st("l_x"), st("u_x"))
+    else:
+        probs = [P.box_only(n, 3000 + i) for i in range(count)]
+        st = lambda key: np.stack([getattr(q, key) for q in probs])
+        bp = z.Problem(st("Q"), st("c"), None, None, None, None, None, st("l_x"), st("u_x"))
+    bs = z.BatchSolver(bp, count, z.Options(reduction=reduction))
+    res, ms = bs.solve()
+    xs = bs.x()
+    bs.close()
+    for i, q in enumerate(probs):
+        tr = ol.port_solve(q, steps=False)
+        assert res[i].iterations == tr.iterations, (i, res[i].iterations, tr.iterations)
+        assert res[i].converged == bool(tr.converged)
+        assert abs(res[i].f - tr.f[tr.iterations]) <= F_TOL * max(1.0, abs(tr.f[tr.iterations]))
+        assert np.max(np.abs(xs[i] - tr.iterate[:n])) < 1e-6
+
+
 def test_error_conventions(z):
     """Reference: ASSERT(l < u) (EnvironmentBuilder.cpp:10-17) and solve_indefinite_ == ASSERT(false)."""
     p = CASES["box_30"]()
