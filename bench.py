@@ -452,7 +452,7 @@ def bench_configs(z, args, local):
     """cfg1 (n=200, m_eq=100, box; normal-equations reduction), cfg2 (n=2048, m=1024; augmented quasi-definite LDL^T)
     and cfg5 (n=4096 portfolio, eps=1e-6; augmented): whole solve from pinned host buffers through the C ABI
     (ipmz_create: H2D; ipmz_solve; ipmz_get_iterate: D2H), best of 4 after one warm-up."""
-    import problems as P
+    import workloads as P  # plain numpy generators at the repo root: the GPU arm imports nothing from tests/ or oracle/
     cases = [("cfg1", "n=200 m_eq=100 eq(SlackedSlacks)+box, normal equations", lambda: P.eq_box(200, 100, 1), z.NORMAL),
              ("cfg2", "n=2048 m=1024 ineq+box, augmented quasi-definite LDL^T", lambda: P.ineq_box(2048, 1024, 2, kind="shift"),
               z.AUGMENTED),
@@ -527,7 +527,7 @@ def batched_cpu_baseline(per_core=2):
 
 
 def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
-    import problems as P
+    import workloads as P  # the GPU arm's inputs; the CPU baseline / parity gate below wrap the same arrays for the oracle
     import torch
     total = CFG4["count"] if not args.quick else 64
     n, m = CFG4["n"], CFG4["m"]
@@ -633,9 +633,10 @@ def bench_batched(z, args, world, rank, local, barrier, allmax, allsum):
             cpu, gate_its = batched_cpu_baseline()
             out["cpu_baseline"] = cpu
             import oracle_lib as ol
+            import problems as PO
             dfs = []
             for i in range(16):
-                q = P.ineq_box(n, m, CFG4["seed0"] + i, kind="shift")
+                q = PO.ineq_box(n, m, CFG4["seed0"] + i, kind="shift")
                 tr = ol.port_solve(q, steps=False)
                 dfs.append(abs(fs[i] - tr.f[tr.iterations]) / max(1.0, abs(tr.f[tr.iterations])))
                 gate_its[i] = tr.iterations
