@@ -265,6 +265,26 @@ def test_batch_ragged_shapes_match_oracle(z, n, m, reduction):
         assert np.max(np.abs(xs[i] - tr.iterate[:n])) < 1e-6
 
 
+@pytest.mark.parametrize("cap", [0, 1, 3])
+def test_batch_iteration_cap(z, cap):
+    """The iteration cap inside the persistent batch kernel (Optimizer.cpp:125: the loop just ends): every problem
+    stops after `cap` iterations, unconverged, with the iterate the oracle has at that point, and the kernel's queue
+    drains (a problem that hits the cap leaves it like one that converged)."""
+    count, n, m = 9, 40, 16
+    probs = [P.ineq_box(n, m, 5000 + i, kind="shift") for i in range(count)]
+    st = lambda key: np.stack([getattr(q, key) for q in probs])
+    bp = z.Problem(st("Q"), st("c"), st("A"), st("l_A"), st("u_A"), None, None, st("l_x"), st("u_x"))
+    bs = z.BatchSolver(bp, count, z.Options(reduction=z.AUGMENTED, max_iter=cap))
+    res, ms = bs.solve()
+    xs = bs.x()
+    bs.close()
+    for i, q in enumerate(probs):
+        assert res[i].iterations == cap and not res[i].converged
+        if cap > 0:
+            tr = ol.port_solve(q, cap_iters=cap, stop_after_cap=True, steps=False)
+            assert np.max(np.abs(xs[i] - tr.iterate[:n])) < 1e-9
+
+
 def test_error_conventions(z):
     """Reference: ASSERT(l < u) (EnvironmentBuilder.cpp:10-17) and solve_indefinite_ == ASSERT(false)."""
     p = CASES["box_30"]()
