@@ -402,6 +402,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   w->tw.cap_blocks = (v.N + 63) / 64;
   ALLOC(w->tw.flags, C * w->tw.cap_blocks); ALLOC(w->tw.ticket, 1);
   w->fused_queue_cap = batch_handle ? fused_work_words(count, opt.max_iter) : 0;
+  if (w->fused_queue_cap > ((size_t)64 << 20)) w->fused_queue_cap = 0;  // absurd iteration caps: problem-granular tickets
   ALLOC(w->fused_ticket, std::max<size_t>(8, w->fused_queue_cap));
   ALLOC(w->ready_dev, 1); ALLOC(w->abort_dev, 1);
   if (count == 1) ALLOC(w->Rlast, v.sp);
