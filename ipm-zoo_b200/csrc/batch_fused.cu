@@ -1,33 +1,36 @@
 // ipm-zoo_b200/csrc/batch_fused.cu -- batches of small QPs (cfg4): the WHOLE Mehrotra predictor-corrector solve of
-// one problem inside one persistent CTA, one launch per batch.
+// every problem of a batch inside one persistent kernel, one launch per batch.
 //
 // Reference control flow per problem: Optimizer::solve_quasi_definite_ (Optimizer.cpp:77-220) with
 // LinearSolvers::ldlt_decomposition / overwriting_solve_ldlt (LinearSolvers.cpp:14-74).  The multi-kernel batched
 // schedule (solver.cu: ~110 launches per iteration, a host synchronisation per iteration to read the stopping test,
 // every matrix pass re-streamed from HBM by a fresh grid) is replaced for systems that fit by:
 //
-//   * a persistent grid (2 CTAs per SM); each CTA takes a problem from a device-side FIFO and runs one complete Mehrotra
+//   * a persistent grid (2 CTAs per SM); a CTA takes a problem from a device-side queue and runs one complete Mehrotra
 //     iteration of it -- matvecs, residuals, stopping test, assembly, LDL^T, both Newton solves (with the normal
-//     reduction's iterative refinement), centring, step length and update -- then hands the problem back to the queue,
-//     so there is no host round trip and no wave quantisation: the batch advances round robin, problems that converge
-//     leave the queue (see "work distribution" below);
-//   * two co-resident CTAs per SM are always in different phases, so the latency-bound chains of one problem (the
-//     one-warp 32 x 32 LDL^T of a diagonal block, the triangular sweeps, block reductions) overlap the DMMA-bound
+//     reduction's iterative refinement), centring, step length and update -- then hands the problem back, so there is
+//     no host round trip and no wave quantisation: the batch advances as one front (fewest iterations first), problems
+//     that converge leave the queue (see "work distribution" below);
+//   * two co-resident CTAs per SM are in different phases most of the time, so the latency-bound chains of one problem
+//     (the one-warp 32 x 32 LDL^T of a diagonal block, the triangular sweeps, block reductions) overlap the DMMA-bound
 //     phases of the other (condensed assembly M^T W M, trailing updates);
-//   * the matrix K / its factor L of a problem is touched by one SM only and stays in L2 between the phases of an
-//     iteration; Q, M and M^T are read-only and re-read from L2 while the problem is in flight.
+//   * the matrix K / its factor L of a problem is stored tile-major (64 x 64 tiles, each contiguous) and touched by one
+//     SM per iteration; Q and M are read-only; the transposed copy M^T the grid-per-phase kernels use is never read.
 //
 // Phases of one iteration (all vector formulas are the bodies of vector_bodies.cuh, shared with the grid-per-phase
 // kernels):
-//   matvecs            Q x, M x, M^T lambda: one warp per row, four rows in flight per warp
+//   matvecs            Q x, M x, M^T lambda: rows staged by bulk copies (cp.async.bulk + mbarrier), 16 lanes per row;
+//                      M^T v accumulated by columns from the same staged rows (M x and M^T lambda are one pass)
 //   residuals          r_*, W, objective, ||res||, mu, stopping test, predictor right-hand side
 //   assembly           NORMAL: K = Q + Y^-1 L_y + Z^-1 L_z + M^T W M on the FP64 tensor pipe (64 x 64 tiles, accumulators
-//                      start from Q, 16-wide k-slices of M^T through a 3-stage cp.async ring that runs across tile
-//                      boundaries, the W scaling folded into the B fragment); AUGMENTED: a copy pass
+//                      start from Q, 16-row slices of M through a 3-stage cp.async ring that runs across tile
+//                      boundaries, fragments read down the slice columns, the W scaling folded into the B fragment);
+//                      AUGMENTED: a copy pass
 //   factorization      right-looking LDL^T, 32-wide panels: panel in shared memory, diagonal block by one warp
 //                      (warp_ldlt32), rows below on the tensor pipe with the 8 x 8 inverse blocks (panel_solve32),
 //                      trailing matrix updated in L2 with both operands read from the shared-memory panel
-//   solves             forward / pivots / backward with x in shared memory, 64-row blocks
+//   solves             forward / pivots / backward over the factor's 64 x 64 tiles (one bulk copy each, 2-stage
+//                      mbarrier ring), x in shared memory, diagonal tiles by 4-column substitution blocks of one warp
 //   back-substitution  eliminated Delta's, ratio test, centring parameter, corrector right-hand side, update
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -618,10 +621,10 @@ __device__ void ldlt_panels(double* K, double* Dg, int N, double* sm) {
 // ---- solves -----------------------------------------------------------------------------------------------------
 // x <- L^-1 x, x <- x / D, x <- L^-T x with the in-place factor; x (global, length N) is staged in shared memory.
 // The factor is consumed as 64 x 64 tiles in ONE fixed sequence -- forward (0,0) (1,0) (1,1) (2,0) ... (b,b), then the
-// same tiles in reverse order for the transposed sweep -- through a 3-stage cp.async ring that runs two tiles ahead of
-// the arithmetic across block-row and sweep boundaries: the only exposed memory round trip of a solve is the first one
-// (the previous version loaded every diagonal block and every off-diagonal strip on demand: 16 exposed L2 / HBM
-// latencies per solve).  Off-diagonal tiles are 64 x 64 matrix-vector products over all 256 threads (4 lanes per row /
+// same tiles in reverse order for the transposed sweep -- through a ring of SOLVE_STAGES shared-memory stages filled by
+// one bulk copy per tile (tile-major factor), one tile ahead of the arithmetic across block-row and sweep boundaries (a
+// third stage costs L1: 91.0 vs 86.4 ms; the first version loaded every diagonal block and every off-diagonal strip on
+// demand: 16 exposed L2 / HBM latencies per solve).  Off-diagonal tiles are 64 x 64 matrix-vector products over all 256 threads (4 lanes per row /
 // column, shuffle reduction); a diagonal tile is the substitution chain of one warp, four columns per step.
 // sm: sx[nblk * 64] | SOLVE_STAGES tiles [64 x TP].
 #ifndef IPMZ_SOLVE_STAGES
