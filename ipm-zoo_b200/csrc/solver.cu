@@ -187,6 +187,20 @@ struct Workspace {
     if (rc == IPMZ_OK) allocs.push_back(*p);
     return rc;
   }
+  // like alloc, with the zero-fill ORDERED ON THE HANDLE'S STREAM: for the buffers the upload writes next on that
+  // stream (the legacy-stream memset of alloc() is not ordered against a non-blocking stream)
+  template <class T>
+  int alloc_st(T** p, size_t n) {
+    if (pooled || !st) return alloc(p, n);
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(IPMZ_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(*p);
+    e = cudaMemsetAsync(*p, 0, n * sizeof(T), st);
+    if (e != cudaSuccess) return fail(IPMZ_ERR_CUDA, std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+    return IPMZ_OK;
+  }
 };
 
 static int check_problem(const ipmz_problem* p) {
@@ -362,6 +376,20 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
     const char* e = getenv("IPMZ_POOL_ALLOC");  // opt-in: measured create 22-27 ms either way at cfg3 size (the 806 MB
     w->pooled = e && atoi(e) != 0;               // upload dominates) and the pool's first allocation costs 650 ms
   }
+  CUDA_TRY(cudaEventCreate(&w->ev0));
+  CUDA_TRY(cudaEventCreate(&w->ev1));
+  const size_t C = (size_t)count;
+#define ALLOC(ptr, n) if ((rc = w->alloc(&(ptr), (n)))) return rc
+#define ALLOC_ST(ptr, n) if ((rc = w->alloc_st(&(ptr), (n)))) return rc
+  // The problem data first: its buffers, zero-filled on the handle's stream, then the H2D copies and the transpose on
+  // that stream.  The copy engine then works (15 ms for cfg3's 806 MB) while the host builds the factorization plans
+  // and allocates the rest below.
+  ALLOC_ST(w->Q, C * v.sQ); ALLOC_ST(w->M, C * v.sM); ALLOC_ST(w->MT, C * v.sMT);
+  ALLOC_ST(w->c, C * s.ns); ALLOC_ST(w->lx, C * s.ns); ALLOC_ST(w->ux, C * s.ns);
+  ALLOC_ST(w->lo, C * s.ms); ALLOC_ST(w->up, C * s.ms);
+  v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
+  if ((rc = upload_data(*w, p))) return rc;
+  lap("data buffers + H2D issued");
   if (count == 1) {
     const int le = lookahead_create(&w->la);
     if (le != 0) return fail(IPMZ_ERR_CUDA, std::string("lookahead_create: ") + cudaGetErrorString((cudaError_t)le));
@@ -374,14 +402,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
       }
     }
   }
-  CUDA_TRY(cudaEventCreate(&w->ev0));
-  CUDA_TRY(cudaEventCreate(&w->ev1));
-  lap("streams + plans");
-  const size_t C = (size_t)count;
-#define ALLOC(ptr, n) if ((rc = w->alloc(&(ptr), (n)))) return rc
-  ALLOC(w->Q, C * v.sQ); ALLOC(w->M, C * v.sM); ALLOC(w->MT, C * v.sMT);
-  ALLOC(w->c, C * s.ns); ALLOC(w->lx, C * s.ns); ALLOC(w->ux, C * s.ns);
-  ALLOC(w->lo, C * s.ms); ALLOC(w->up, C * s.ms);
+  lap("plans");
   ALLOC(v.V, C * v.sp); ALLOC(v.D, C * v.sp); ALLOC(v.DA, C * v.sp); ALLOC(v.R, C * v.sp);
   ALLOC(v.Qx, C * s.ns); ALLOC(v.MTl, C * s.ns); ALLOC(v.tn, C * s.ns);
   ALLOC(v.Mx, C * s.ms); ALLOC(v.winv, C * s.ms); ALLOC(v.W, C * s.ms); ALLOC(v.tm, C * s.ms);
@@ -408,7 +429,7 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   if (count == 1) ALLOC(w->Rlast, v.sp);
   if (opt.record_steps && count == 1) ALLOC(w->steps_dev, (size_t)std::max(1, opt.max_iter) * 2 * w->Naug);
 #undef ALLOC
-  v.Q = w->Q; v.M = w->M; v.MT = w->MT; v.c = w->c; v.lx = w->lx; v.ux = w->ux; v.lo = w->lo; v.up = w->up;
+#undef ALLOC_ST
   v.active = nullptr;
   {
     const char* e = getenv("IPMZ_BATCH_FUSED");
@@ -417,13 +438,15 @@ static int create_workspace(Workspace** out, int count, const ipmz_problem* p, c
   lap("device allocations + memset");
   if (!w->sc_host.resize(count)) return fail(IPMZ_ERR_ALLOC, "cudaHostAlloc of the Scal mirror failed");
   w->active_host.resize(count);
-
   lap("pinned Scal mirror");
-  if ((rc = upload_data(*w, p))) return rc;
+  // the zero-fills of alloc() run on the legacy stream: everything the handle's (non-blocking) stream does from here
+  // on -- the initial point now, every solve later -- is ordered after them
+  CUDA_TRY(cudaEventRecord(w->ev0, cudaStreamLegacy));
+  CUDA_TRY(cudaStreamWaitEvent(w->st, w->ev0, 0));
   launch_initial_point(w->st, v, count);
   CUDA_TRY(cudaStreamSynchronize(w->st));
   CUDA_TRY(cudaGetLastError());
-  lap("H2D + transpose + initial point");
+  lap("H2D + transpose + initial point (wait)");
   guard.release();
   *out = w;
   return IPMZ_OK;

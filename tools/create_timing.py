@@ -11,7 +11,7 @@ pin = {}
 for k in ("Q", "c", "A", "l_A", "u_A", "l_x", "u_x"):
     pin[k] = z.pinned_empty(getattr(q, k).shape); pin[k][...] = getattr(q, k)
 pr = z.Problem(pin["Q"], pin["c"], pin["A"], pin["l_A"], pin["u_A"], None, None, pin["l_x"], pin["u_x"])
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", "3"))):
     t0 = time.perf_counter(); s = z.Solver(pr, z.Options(reduction=z.NORMAL))
     t1 = time.perf_counter(); r = s.solve()
     t2 = time.perf_counter(); it = s.iterate()
